@@ -1,0 +1,729 @@
+// drone2d.cu -- kernels + C ABI (include/drone2d.h) of the batched Drone2dEnv step.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -shared -Xcompiler -fPIC
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "drone2d_device.cuh"
+
+#ifndef D2D_BLOCK
+#define D2D_BLOCK 128
+#endif
+#ifndef D2D_MIN_BLOCKS
+#define D2D_MIN_BLOCKS 3
+#endif
+
+using namespace d2d;
+
+// ===========================================================================
+// kernels
+// ===========================================================================
+
+template <bool PER_ENV>
+struct ViewOf;
+template <>
+struct ViewOf<true> {
+    typedef EnvView type;
+    static __device__ __forceinline__ EnvView make(const D2dParams &p, const D2dSharedTables *, int64_t i, int n_obs)
+    {
+        return EnvView{&p, i, n_obs};
+    }
+};
+template <>
+struct ViewOf<false> {
+    typedef SharedView type;
+    static __device__ __forceinline__ SharedView make(const D2dParams &, const D2dSharedTables *t, int64_t, int)
+    {
+        return SharedView{t};
+    }
+};
+
+__device__ __forceinline__ void stage_shared_tables(const D2dParams &p, D2dSharedTables *dst, int tid, int nthreads)
+{
+    const int *src = reinterpret_cast<const int *>(p.shared);
+    int *d = reinterpret_cast<int *>(dst);
+    for (int k = tid; k < (int)(sizeof(D2dSharedTables) / sizeof(int)); k += nthreads) d[k] = src[k];
+}
+
+// The fused step: thrust -> cpSpaceStep -> sensor overlap -> nearest-3 ->
+// closest/look-ahead point -> 27-float observation -> reward -> termination ->
+// episode statistics -> auto-reset (+ first observation of the new episode).
+template <bool PER_ENV>
+__global__ void __launch_bounds__(D2D_BLOCK, D2D_MIN_BLOCKS) d2d_step_kernel(const __grid_constant__ D2dParams p)
+{
+    __shared__ float s_obs[D2D_BLOCK * D2D_OBS_DIM];
+    __shared__ double s_stats[D2D_STATS_DOUBLES];
+    __shared__ int s_any_done;
+    __shared__ D2dSharedTables s_tab;
+
+    const int tid = threadIdx.x;
+    const int64_t i = (int64_t)blockIdx.x * D2D_BLOCK + tid;
+    const bool valid = i < p.n;
+    const D2dConst &c = p.c;
+
+    if (!PER_ENV) stage_shared_tables(p, &s_tab, tid, D2D_BLOCK);
+    if (tid < D2D_STATS_DOUBLES) s_stats[tid] = 0.0;
+    if (tid == 0) s_any_done = 0;
+    __syncthreads();
+
+    if (valid) {
+        EnvState s;
+        load_state(p, i, s);
+
+        float2 act;
+        if (p.actions) {
+            act = reinterpret_cast<const float2 *>(p.actions)[i];
+        } else {
+            uint32_t o[4];
+            philox4x32_10((uint32_t)(c.env_id_base + i), (uint32_t)p.step_index, (uint32_t)(p.step_index >> 32),
+                          D2D_STREAM_ACTION, c.seed_lo, c.seed_hi, o);
+            act.x = (float)(2.0 * u01_from_bits(o[0], o[1]) - 1.0);
+            act.y = (float)(2.0 * u01_from_bits(o[2], o[3]) - 1.0);
+        }
+
+        double rc0, rs0;
+        physics_step(s, c, (double)act.x, (double)act.y, rc0, rs0);
+        s.steps += 1;                                               // env:407
+
+        bool second = false;
+        float *row = &s_obs[tid * D2D_OBS_DIM];
+#pragma unroll 1
+        for (;;) {
+            typename ViewOf<PER_ENV>::type v = ViewOf<PER_ENV>::make(p, &s_tab, i, s.n_obs);
+            Nearest nr;
+            const bool hit = scan_obstacles(v, c, s.px[0], s.py[0], rc0, rs0, !second, nr);
+            if (hit) s.flags |= D2D_F_COLLIDED;                     // begin callback, env:17-19
+
+            double *o64 = (p.obs64 && !second) ? p.obs64 + i * D2D_OBS_DIM : nullptr;
+            auto put = [&](int j, double val) {
+                row[j] = (float)val;
+                if (o64) o64[j] = val;
+            };
+            ObsAux ax;
+            observe(v, c, s, rc0, rs0, nr, put, ax);
+            if (second) break;
+
+            StepResult r;
+            reward_and_done(c, s, ax, v.n_obs() > 0, r);
+            p.reward[i] = (float)r.reward;
+            p.done[i] = r.done ? 1 : 0;
+            if (p.info) {
+                double *f = p.info + i * D2D_INFO_DOUBLES;
+                f[0] = r.reward; f[1] = r.r_CA; f[2] = r.r_PA; f[3] = r.r_PP; f[4] = r.r_coll; f[5] = r.r_end;
+                f[6] = r.r_AA; f[7] = (double)s.steps; f[8] = r.d1; f[9] = r.ape; f[10] = s.total_reward;
+                f[11] = (double)r.end_bits; f[12] = ax.u_star; f[13] = (double)ax.nfev;
+                f[14] = (double)ax.near_packed; f[15] = (double)s.episode;
+            }
+            if (!r.done) break;
+
+            if (!(s.flags & D2D_F_DONE)) {
+                // episode statistics (env:593-613; main.py:272-282; tensorboardlogger.py:80-88)
+                const int b = r.end_bits;
+                s_any_done = 1;
+                atomicAdd(&s_stats[0], 1.0);
+                if (b & 2) atomicAdd(&s_stats[1], 1.0);
+                if (b & (1 | 4 | 8)) atomicAdd(&s_stats[2], 1.0);
+                if ((b & 1) && !(b & (2 | 4 | 8))) atomicAdd(&s_stats[3], 1.0);   // later branches overwrite n_collisions
+                atomicAdd(&s_stats[4], (double)s.steps);
+                atomicAdd(&s_stats[5], r.ape);
+                atomicAdd(&s_stats[6], s.total_reward);
+                atomicAdd(&s_stats[7], r.reward);
+                atomicAdd(&s_stats[8], r.r_coll);
+                atomicAdd(&s_stats[9], r.r_CA);
+                atomicAdd(&s_stats[10], r.r_PA);
+                atomicAdd(&s_stats[11], r.r_PP);
+                atomicAdd(&s_stats[12], r.r_end);
+                atomicAdd(&s_stats[13], r.r_AA);
+                p.last[i] = make_double2(s.total_reward, (double)s.steps);
+                p.last[p.np + i] = make_double2(r.ape, (double)b);
+            }
+            if (!p.auto_reset) {
+                s.flags |= D2D_F_DONE;
+                break;
+            }
+            if (p.terminal_obs) {
+                float *t = p.terminal_obs + i * D2D_OBS_DIM;
+#pragma unroll
+                for (int j = 0; j < D2D_OBS_DIM; j++) t[j] = row[j];
+            }
+            reset_env<PER_ENV>(p, i, s, s.episode + 1);
+            sincos(s.an[0], &rs0, &rc0);
+            second = true;
+        }
+        store_state(p, i, s);
+    }
+    __syncthreads();
+
+    // coalesced store of the block's [BLOCK][27] float32 observation tile
+    {
+        const int64_t base = (int64_t)blockIdx.x * D2D_BLOCK;
+        const int rows = (int)min((int64_t)D2D_BLOCK, p.n - base);
+        if (rows == D2D_BLOCK) {
+            const float4 *src = reinterpret_cast<const float4 *>(s_obs);
+            float4 *dst = reinterpret_cast<float4 *>(p.obs + base * D2D_OBS_DIM);
+            for (int k = tid; k < D2D_BLOCK * D2D_OBS_DIM / 4; k += D2D_BLOCK) dst[k] = src[k];
+        } else if (rows > 0) {
+            float *dst = p.obs + base * D2D_OBS_DIM;
+            for (int k = tid; k < rows * D2D_OBS_DIM; k += D2D_BLOCK) dst[k] = s_obs[k];
+        }
+    }
+    if (s_any_done && tid < 14) atomicAdd(&p.stats[tid], s_stats[tid]);
+}
+
+// Drone2dEnv.reset() for all / masked envs: re-spawn + first observation.
+template <bool PER_ENV>
+__global__ void __launch_bounds__(D2D_BLOCK) d2d_reset_kernel(const __grid_constant__ D2dParams p)
+{
+    __shared__ D2dSharedTables s_tab;
+    const int tid = threadIdx.x;
+    const int64_t i = (int64_t)blockIdx.x * D2D_BLOCK + tid;
+    if (!PER_ENV) stage_shared_tables(p, &s_tab, tid, D2D_BLOCK);
+    __syncthreads();
+    if (i >= p.n) return;
+    if (p.mask && !p.mask[i]) return;
+    const D2dConst &c = p.c;
+    EnvState s;
+    load_state(p, i, s);
+    const int episode = (s.flags & D2D_F_INIT) ? s.episode + 1 : 0;
+    reset_env<PER_ENV>(p, i, s, episode);
+    double rc0, rs0;
+    sincos(s.an[0], &rs0, &rc0);
+    typename ViewOf<PER_ENV>::type v = ViewOf<PER_ENV>::make(p, &s_tab, i, s.n_obs);
+    Nearest nr;
+    scan_obstacles(v, c, s.px[0], s.py[0], rc0, rs0, false, nr);
+    float *row = p.obs ? p.obs + i * D2D_OBS_DIM : nullptr;
+    double *o64 = p.obs64 ? p.obs64 + i * D2D_OBS_DIM : nullptr;
+    auto put = [&](int j, double val) {
+        if (row) row[j] = (float)val;
+        if (o64) o64[j] = val;
+    };
+    ObsAux ax;
+    observe(v, c, s, rc0, rs0, nr, put, ax);
+    if (p.info) {
+        double *f = p.info + i * D2D_INFO_DOUBLES;
+        for (int k = 0; k < D2D_INFO_DOUBLES; k++) f[k] = 0.0;
+        f[12] = ax.u_star; f[13] = (double)ax.nfev; f[14] = (double)ax.near_packed; f[15] = (double)s.episode;
+    }
+    store_state(p, i, s);
+}
+
+template <bool PER_ENV>
+__global__ void d2d_closest_u_kernel(const __grid_constant__ D2dParams p, const double *pos, double *u_out, int *nfev_out)
+{
+    __shared__ D2dSharedTables s_tab;
+    const int tid = threadIdx.x;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + tid;
+    if (!PER_ENV) stage_shared_tables(p, &s_tab, tid, blockDim.x);
+    __syncthreads();
+    if (i >= p.n) return;
+    typename ViewOf<PER_ENV>::type v = ViewOf<PER_ENV>::make(p, &s_tab, i, 0);
+    int nfev;
+    u_out[i] = closest_u(v, pos[2 * i], pos[2 * i + 1], nfev);
+    nfev_out[i] = nfev;
+}
+
+// AoS blob <-> SoA state (d2d_get_state / d2d_set_state)
+__global__ void d2d_pack_state_kernel(const D2dParams p, double *blob, int to_blob)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.n) return;
+    double *b = blob + i * D2D_STATE_DOUBLES;
+    EnvState s;
+    if (to_blob) {
+        load_state(p, i, s);
+        for (int k = 0; k < 3; k++) {
+            b[6 * k + 0] = s.px[k]; b[6 * k + 1] = s.py[k]; b[6 * k + 2] = s.vx[k]; b[6 * k + 3] = s.vy[k];
+            b[6 * k + 4] = s.an[k]; b[6 * k + 5] = s.om[k];
+        }
+        for (int j = 0; j < 6; j++) { b[18 + 2 * j] = s.jx[j]; b[19 + 2 * j] = s.jy[j]; }
+        b[30] = (s.flags & D2D_F_COLLIDED) ? 1.0 : 0.0;
+        b[31] = (s.flags & D2D_F_LATCHED) ? 1.0 : 0.0;
+        b[32] = (double)s.steps; b[33] = s.path_error; b[34] = s.total_reward; b[35] = (double)s.episode;
+    } else {
+        load_state(p, i, s);   // keeps n_obs
+        for (int k = 0; k < 3; k++) {
+            s.px[k] = b[6 * k + 0]; s.py[k] = b[6 * k + 1]; s.vx[k] = b[6 * k + 2]; s.vy[k] = b[6 * k + 3];
+            s.an[k] = b[6 * k + 4]; s.om[k] = b[6 * k + 5];
+        }
+        for (int j = 0; j < 6; j++) { s.jx[j] = b[18 + 2 * j]; s.jy[j] = b[19 + 2 * j]; }
+        s.flags = D2D_F_INIT | (b[30] != 0.0 ? D2D_F_COLLIDED : 0) | (b[31] != 0.0 ? D2D_F_LATCHED : 0);
+        s.steps = (int)b[32]; s.path_error = b[33]; s.total_reward = b[34]; s.episode = (int)b[35];
+        store_state(p, i, s);
+    }
+}
+
+// AoS host-layout tables <-> per-env SoA tables (d2d_set_tables / d2d_get_tables)
+__global__ void d2d_pack_tables_kernel(const D2dParams p, double *wps, double *us, double *xp, double *yp, int *n_obs,
+                                       double *obst, int to_host)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.n) return;
+    for (int k = 0; k < D2D_MAX_WPS; k++) {
+        const int64_t r = (int64_t)k * p.np + i;
+        double *w = wps + (i * D2D_MAX_WPS + k) * 2;
+        double *x = xp + (i * D2D_MAX_WPS + k) * 3, *y = yp + (i * D2D_MAX_WPS + k) * 3;
+        if (to_host) {
+            const double2 W = p.wps[r], A = p.pa[r], B = p.pb[r], C = p.pc[r];
+            w[0] = W.x; w[1] = W.y; us[i * D2D_MAX_WPS + k] = p.us[r];
+            x[0] = A.x; x[1] = B.x; x[2] = C.x; y[0] = A.y; y[1] = B.y; y[2] = C.y;
+        } else {
+            p.wps[r] = make_double2(w[0], w[1]); p.us[r] = us[i * D2D_MAX_WPS + k];
+            p.pa[r] = make_double2(x[0], y[0]); p.pb[r] = make_double2(x[1], y[1]); p.pc[r] = make_double2(x[2], y[2]);
+        }
+    }
+    for (int k = 0; k < D2D_MAX_OBS_ENV; k++) {
+        const int64_t r = (int64_t)k * p.np + i;
+        double *o = obst + (i * D2D_MAX_OBS_ENV + k) * 3;
+        if (to_host) {
+            const double2 xy = p.obxy[r];
+            o[0] = xy.x; o[1] = xy.y; o[2] = p.obr[r];
+        } else {
+            p.obxy[r] = make_double2(o[0], o[1]); p.obr[r] = o[2];
+        }
+    }
+    if (to_host) {
+        n_obs[i] = p.meta[i].w;
+    } else {
+        int4 m = p.meta[i];
+        m.w = n_obs[i];
+        p.meta[i] = m;
+    }
+}
+
+// ===========================================================================
+// host side: handle + C ABI
+// ===========================================================================
+
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                            \
+    do {                                                                                          \
+        cudaError_t e_ = (expr);                                                                  \
+        if (e_ != cudaSuccess) return fail(D2D_ECUDA, "%s: %s", #expr, cudaGetErrorString(e_));  \
+    } while (0)
+
+struct d2d_env {
+    d2d_config cfg;
+    D2dLayout lay;
+    D2dParams p;                 // template parameter block (I/O pointers filled per call)
+    int device;
+    bool tables_set;             // test mode: scenario uploaded
+    D2dSharedTables *shared_dev;
+    double *stats_dev;
+    uint64_t step_index;
+    int64_t launches;
+    // host-boundary staging (d2d_step_host)
+    float *h_act, *h_obs, *h_rew;
+    uint8_t *h_done;
+    float *d_act, *d_obs, *d_rew;
+    uint8_t *d_done;
+};
+
+struct DeviceGuard {
+    int prev;
+    bool switched;
+    explicit DeviceGuard(int dev) : prev(-1), switched(false)
+    {
+        if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) switched = (cudaSetDevice(dev) == cudaSuccess);
+    }
+    ~DeviceGuard()
+    {
+        if (switched) cudaSetDevice(prev);
+    }
+};
+
+// cpMomentForPoly on the box vertices Poly.create_box produces (Drone.py:16-17,33-34)
+static double moment_for_box(double m, double w, double h)
+{
+    const double hw = w / 2, hh = h / 2;
+    const double vx[4] = {hw, hw, -hw, -hw}, vy[4] = {-hh, hh, hh, -hh};
+    double sum1 = 0.0, sum2 = 0.0;
+    for (int i = 0; i < 4; i++) {
+        const int j = (i + 1) % 4;
+        const double a = vx[j] * vy[i] - vy[j] * vx[i];
+        const double b = (vx[i] * vx[i] + vy[i] * vy[i]) + (vx[i] * vx[j] + vy[i] * vy[j]) + (vx[j] * vx[j] + vy[j] * vy[j]);
+        sum1 += a * b;
+        sum2 += a;
+    }
+    return (m * sum1) / (6.0 * sum2);
+}
+
+static int check_config(const d2d_config *c)
+{
+    if (!c) return fail(D2D_EINVAL, "config is NULL");
+    if (c->abi_version != D2D_ABI_VERSION) return fail(D2D_EINVAL, "abi_version %d != %d", c->abi_version, D2D_ABI_VERSION);
+    if (c->mode != D2D_MODE_TEST && c->mode != D2D_MODE_CURRICULUM) return fail(D2D_EINVAL, "mode must be 0 (test) or 1 (curriculum)");
+    if (c->mode == D2D_MODE_CURRICULUM) {
+        if (c->stage < 1 || c->stage > 5) return fail(D2D_EINVAL, "stage must be 1..5 in curriculum mode");
+        if (c->n_wps < 4 || c->n_wps > D2D_MAX_WPS) return fail(D2D_EINVAL, "n_wps must be in [4, %d]", D2D_MAX_WPS);
+        if (c->spawn_corner_lo < 1 || c->spawn_corner_hi > 4 || c->spawn_corner_lo > c->spawn_corner_hi)
+            return fail(D2D_EINVAL, "spawn_corners must satisfy 1 <= lo <= hi <= 4");
+    }
+    if (c->n_steps < 1) return fail(D2D_EINVAL, "n_steps must be >= 1");
+    if (c->iterations < 1 || c->iterations > 1000) return fail(D2D_EINVAL, "iterations out of range");
+    if (!(c->dt > 0) || !(c->mass_f > 0) || !(c->mass_m > 0) || !(c->width > c->height) || !(c->height > 6))
+        return fail(D2D_EINVAL, "drone constants out of range");
+    if (!(c->screen_x > 0) || !(c->screen_y > 0)) return fail(D2D_EINVAL, "screen size must be positive");
+    return D2D_OK;
+}
+
+static void derive_constants(const d2d_config *g, D2dConst *c, uint64_t seed, int64_t env_id_base)
+{
+    memset(c, 0, sizeof *c);
+    c->mode = g->mode; c->stage = g->stage; c->n_steps = g->n_steps; c->n_wps = g->n_wps;
+    c->corner_lo = g->spawn_corner_lo; c->corner_hi = g->spawn_corner_hi; c->random_path_spawn = g->random_path_spawn;
+    c->use_Lambda = g->use_Lambda; c->iterations = g->iterations;
+    c->W = g->screen_x; c->H = g->screen_y; c->seg_len = g->path_segment_length; c->lookahead = g->lookahead;
+    c->danger_range = g->danger_range; c->danger_angle = g->danger_angle; c->k_ca = g->abs_inv_CA_min_rew;
+    c->PA_band_edge = g->PA_band_edge; c->PA_scale = g->PA_scale; c->PP_vel_scale = g->PP_vel_scale;
+    c->PP_rew_max = g->PP_rew_max; c->PP_rew_min = g->PP_rew_min; c->rew_collision = g->rew_collision;
+    c->reach_end_radius = g->reach_end_radius; c->rew_reach_end = g->rew_reach_end;
+    c->AA_angle = g->AA_angle; c->AA_band = g->AA_band; c->rew_AA = g->rew_AA;
+    c->spawn_chance = g->stage_spawn_chance;
+    c->sp_xmin = g->spawn_xmin; c->sp_xmax = g->spawn_xmax; c->sp_ymin = g->spawn_ymin; c->sp_ymax = g->spawn_ymax;
+    c->gx = g->gravity_x; c->gy = g->gravity_y; c->dt = g->dt; c->force_scale = g->force_scale;
+    c->R = g->width / 2 - g->height / 2;                      // Drone.py:11
+    c->d = g->height / 2 - 3;                                 // Drone.py:10
+    c->hw = g->width / 2; c->hh = (g->height / 2) / 2;        // frame box (width, height/2), Drone.py:16
+    c->minv_f = 1.0 / g->mass_f; c->minv_m = 1.0 / g->mass_m;
+    c->iinv_f = 1.0 / moment_for_box(g->mass_f, g->width, g->height / 2);
+    c->iinv_m = 1.0 / moment_for_box(g->mass_m, g->height, g->height);
+    c->msum = c->minv_m + c->minv_f;
+    c->bias_coef = -(1.0 - pow(0.0, g->dt)) / g->dt;          // error_bias = 0 (Drone.py:64)
+    c->diag = sqrt(g->screen_x * g->screen_x + g->screen_y * g->screen_y);
+    c->seed_lo = (uint32_t)seed; c->seed_hi = (uint32_t)(seed >> 32);
+    c->env_id_base = env_id_base;
+}
+
+extern "C" {
+
+int d2d_abi_version(void) { return D2D_ABI_VERSION; }
+const char *d2d_last_error(void) { return g_err; }
+
+int d2d_default_config(d2d_config *c)
+{
+    if (!c) return fail(D2D_EINVAL, "config is NULL");
+    memset(c, 0, sizeof *c);
+    c->abi_version = D2D_ABI_VERSION;
+    c->mode = D2D_MODE_CURRICULUM; c->stage = 1;
+    c->n_steps = 1100; c->n_wps = 12; c->spawn_corner_lo = 1; c->spawn_corner_hi = 4; c->random_path_spawn = 1;
+    c->use_Lambda = 1; c->iterations = 10;
+    c->screen_x = 1300; c->screen_y = 1300; c->path_segment_length = 100; c->lookahead = 220;
+    c->danger_range = 150; c->danger_angle = 20; c->abs_inv_CA_min_rew = 1.0 / 8;
+    c->PA_band_edge = 40; c->PA_scale = 2; c->PP_vel_scale = 0.08; c->PP_rew_max = 2.5; c->PP_rew_min = -1;
+    c->rew_collision = -50; c->reach_end_radius = 20; c->rew_reach_end = 30;
+    c->AA_angle = M_PI / 2; c->AA_band = M_PI / 4; c->rew_AA = -1;
+    c->stage_spawn_chance = 0.6;
+    c->spawn_xmin = 50; c->spawn_xmax = 250; c->spawn_ymin = 150; c->spawn_ymax = 1000;
+    c->mass_f = 0.2; c->mass_m = 0.4; c->width = 100; c->height = 20;
+    c->gravity_x = 0; c->gravity_y = -1000; c->dt = 1.0 / 60; c->force_scale = 1000;
+    return D2D_OK;
+}
+
+int d2d_state_bytes(const d2d_config *cfg, int64_t n_envs, size_t *bytes)
+{
+    int rc = check_config(cfg);
+    if (rc) return rc;
+    if (n_envs < 1 || !bytes) return fail(D2D_EINVAL, "n_envs must be >= 1 and bytes non-NULL");
+    D2dLayout L;
+    d2d_make_layout(&L, n_envs, cfg->mode == D2D_MODE_CURRICULUM);
+    *bytes = L.bytes;
+    return D2D_OK;
+}
+
+int d2d_create(const d2d_config *cfg, int64_t n_envs, int64_t env_id_base, uint64_t seed, int device,
+               void *state_dev, size_t state_bytes, d2d_env **out)
+{
+    int rc = check_config(cfg);
+    if (rc) return rc;
+    if (!out || !state_dev || n_envs < 1) return fail(D2D_EINVAL, "bad arguments to d2d_create");
+    if (((uintptr_t)state_dev & 255) != 0) return fail(D2D_EINVAL, "state_dev must be 256-byte aligned");
+    D2dLayout L;
+    d2d_make_layout(&L, n_envs, cfg->mode == D2D_MODE_CURRICULUM);
+    if (state_bytes < L.bytes) return fail(D2D_EINVAL, "state buffer too small: %zu < %zu", state_bytes, L.bytes);
+    DeviceGuard guard(device);
+    d2d_env *e = new (std::nothrow) d2d_env();
+    if (!e) return fail(D2D_EINVAL, "out of host memory");
+    memset(e, 0, sizeof *e);
+    e->cfg = *cfg; e->lay = L; e->device = device;
+    char *base = (char *)state_dev;
+    D2dParams &p = e->p;
+    p.n = L.n; p.np = L.np;
+    p.pos = (double2 *)(base + L.off_pos); p.vel = (double2 *)(base + L.off_vel); p.ang = (double2 *)(base + L.off_ang);
+    p.jacc = (double2 *)(base + L.off_jacc); p.acc = (double2 *)(base + L.off_acc); p.meta = (int4 *)(base + L.off_meta);
+    p.last = (double2 *)(base + L.off_last);
+    if (L.per_env_tables) {
+        p.us = (double *)(base + L.off_us); p.wps = (double2 *)(base + L.off_wps);
+        p.pa = (double2 *)(base + L.off_pa); p.pb = (double2 *)(base + L.off_pb); p.pc = (double2 *)(base + L.off_pc);
+        p.obxy = (double2 *)(base + L.off_obxy); p.obr = (double *)(base + L.off_obr);
+    }
+    derive_constants(cfg, &p.c, seed, env_id_base);
+    cudaError_t err = cudaMalloc(&e->shared_dev, sizeof(D2dSharedTables));
+    if (err == cudaSuccess) err = cudaMalloc(&e->stats_dev, D2D_STATS_DOUBLES * sizeof(double));
+    if (err == cudaSuccess) err = cudaMemset(e->stats_dev, 0, D2D_STATS_DOUBLES * sizeof(double));
+    if (err == cudaSuccess) err = cudaMemset(e->shared_dev, 0, sizeof(D2dSharedTables));
+    if (err == cudaSuccess) err = cudaMemset(state_dev, 0, L.bytes);
+    if (err != cudaSuccess) {
+        cudaFree(e->shared_dev); cudaFree(e->stats_dev);
+        delete e;
+        return fail(D2D_ECUDA, "d2d_create: %s", cudaGetErrorString(err));
+    }
+    p.shared = e->shared_dev;
+    p.stats = e->stats_dev;
+    e->tables_set = (cfg->mode == D2D_MODE_CURRICULUM);
+    *out = e;
+    return D2D_OK;
+}
+
+int d2d_destroy(d2d_env *e)
+{
+    if (!e) return D2D_OK;
+    DeviceGuard guard(e->device);
+    cudaFree(e->shared_dev); cudaFree(e->stats_dev);
+    cudaFree(e->d_act); cudaFree(e->d_obs); cudaFree(e->d_rew); cudaFree(e->d_done);
+    cudaFreeHost(e->h_act); cudaFreeHost(e->h_obs); cudaFreeHost(e->h_rew); cudaFreeHost(e->h_done);
+    delete e;
+    return D2D_OK;
+}
+
+int d2d_set_scenario(d2d_env *e, int n_wps, const double *wps, const double *us, const double *xparams,
+                     const double *yparams, int n_obs, const double *obstacles, void *stream)
+{
+    if (!e) return fail(D2D_EINVAL, "handle is NULL");
+    if (e->cfg.mode != D2D_MODE_TEST) return fail(D2D_ESTATE, "d2d_set_scenario needs mode = test");
+    if (n_wps < 4 || n_wps > D2D_MAX_WPS) return fail(D2D_EINVAL, "n_wps must be in [4, %d]", D2D_MAX_WPS);
+    if (n_obs < 0 || n_obs > D2D_MAX_OBS_SHARED) return fail(D2D_EINVAL, "n_obs must be in [0, %d]", D2D_MAX_OBS_SHARED);
+    if (!wps || !us || !xparams || !yparams || (n_obs > 0 && !obstacles)) return fail(D2D_EINVAL, "NULL table pointer");
+    for (int k = 1; k < n_wps; k++)
+        if (!(us[k] > us[k - 1])) return fail(D2D_EINVAL, "us must be strictly increasing");
+    DeviceGuard guard(e->device);
+    D2dSharedTables t;
+    memset(&t, 0, sizeof t);
+    t.n_wps = n_wps; t.n_obs = n_obs;
+    for (int k = 0; k < n_wps; k++) { t.us[k] = us[k]; t.wx[k] = wps[2 * k]; t.wy[k] = wps[2 * k + 1]; }
+    for (int r = 0; r < n_wps - 2; r++) {
+        t.ax[r] = xparams[3 * r]; t.bx[r] = xparams[3 * r + 1]; t.cx[r] = xparams[3 * r + 2];
+        t.ay[r] = yparams[3 * r]; t.by[r] = yparams[3 * r + 1]; t.cy[r] = yparams[3 * r + 2];
+    }
+    for (int k = 0; k < n_obs; k++) { t.ox[k] = obstacles[3 * k]; t.oy[k] = obstacles[3 * k + 1]; t.orad[k] = obstacles[3 * k + 2]; }
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(cudaMemcpyAsync(e->shared_dev, &t, sizeof t, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaStreamSynchronize(st));   // t lives on this stack frame
+    e->p.c.n_wps = n_wps;
+    e->tables_set = true;
+    return D2D_OK;
+}
+
+static int grid_for(int64_t n, int block) { return (int)((n + block - 1) / block); }
+
+static int launch_tables_kernel(d2d_env *e, double *wps, double *us, double *xp, double *yp, int32_t *n_obs,
+                                double *obst, int to_host)
+{
+    const int64_t n = e->lay.n;
+    const size_t b_w = n * D2D_MAX_WPS * 2 * 8, b_u = n * D2D_MAX_WPS * 8, b_p = n * D2D_MAX_WPS * 3 * 8;
+    const size_t b_n = n * 4, b_o = n * D2D_MAX_OBS_ENV * 3 * 8;
+    char *buf = nullptr;
+    const size_t total = b_w + b_u + 2 * b_p + b_o + d2d_align_up(b_n, 8);
+    CUDA_TRY(cudaMalloc(&buf, total));
+    double *dw = (double *)buf, *du = (double *)(buf + b_w), *dx = (double *)(buf + b_w + b_u);
+    double *dy = (double *)(buf + b_w + b_u + b_p), *dob = (double *)(buf + b_w + b_u + 2 * b_p);
+    int *dn = (int *)(buf + b_w + b_u + 2 * b_p + b_o);
+    cudaError_t err = cudaSuccess;
+    if (!to_host) {
+        err = cudaMemcpy(dw, wps, b_w, cudaMemcpyHostToDevice);
+        if (!err) err = cudaMemcpy(du, us, b_u, cudaMemcpyHostToDevice);
+        if (!err) err = cudaMemcpy(dx, xp, b_p, cudaMemcpyHostToDevice);
+        if (!err) err = cudaMemcpy(dy, yp, b_p, cudaMemcpyHostToDevice);
+        if (!err) err = cudaMemcpy(dob, obst, b_o, cudaMemcpyHostToDevice);
+        if (!err) err = cudaMemcpy(dn, n_obs, b_n, cudaMemcpyHostToDevice);
+    }
+    if (!err) {
+        d2d_pack_tables_kernel<<<grid_for(n, 128), 128>>>(e->p, dw, du, dx, dy, dn, dob, to_host);
+        e->launches++;
+        err = cudaGetLastError();
+        if (!err) err = cudaDeviceSynchronize();
+    }
+    if (!err && to_host) {
+        err = cudaMemcpy(wps, dw, b_w, cudaMemcpyDeviceToHost);
+        if (!err) err = cudaMemcpy(us, du, b_u, cudaMemcpyDeviceToHost);
+        if (!err) err = cudaMemcpy(xp, dx, b_p, cudaMemcpyDeviceToHost);
+        if (!err) err = cudaMemcpy(yp, dy, b_p, cudaMemcpyDeviceToHost);
+        if (!err) err = cudaMemcpy(obst, dob, b_o, cudaMemcpyDeviceToHost);
+        if (!err) err = cudaMemcpy(n_obs, dn, b_n, cudaMemcpyDeviceToHost);
+    }
+    cudaFree(buf);
+    if (err) return fail(D2D_ECUDA, "table transfer: %s", cudaGetErrorString(err));
+    return D2D_OK;
+}
+
+int d2d_set_tables(d2d_env *e, const double *wps, const double *us, const double *xparams, const double *yparams,
+                   const int32_t *n_obs, const double *obstacles)
+{
+    if (!e) return fail(D2D_EINVAL, "handle is NULL");
+    if (e->cfg.mode != D2D_MODE_CURRICULUM) return fail(D2D_ESTATE, "per-env tables exist only in curriculum mode");
+    if (!wps || !us || !xparams || !yparams || !n_obs || !obstacles) return fail(D2D_EINVAL, "NULL table pointer");
+    for (int64_t i = 0; i < e->lay.n; i++)
+        if (n_obs[i] < 0 || n_obs[i] > D2D_MAX_OBS_ENV) return fail(D2D_EINVAL, "n_obs[%lld] out of range", (long long)i);
+    DeviceGuard guard(e->device);
+    return launch_tables_kernel(e, (double *)wps, (double *)us, (double *)xparams, (double *)yparams, (int32_t *)n_obs,
+                                (double *)obstacles, 0);
+}
+
+int d2d_get_tables(d2d_env *e, double *wps, double *us, double *xparams, double *yparams, int32_t *n_obs, double *obstacles)
+{
+    if (!e) return fail(D2D_EINVAL, "handle is NULL");
+    if (e->cfg.mode != D2D_MODE_CURRICULUM) return fail(D2D_ESTATE, "per-env tables exist only in curriculum mode");
+    if (!wps || !us || !xparams || !yparams || !n_obs || !obstacles) return fail(D2D_EINVAL, "NULL table pointer");
+    DeviceGuard guard(e->device);
+    return launch_tables_kernel(e, wps, us, xparams, yparams, n_obs, obstacles, 1);
+}
+
+int d2d_set_taps(d2d_env *e, double *obs64_dev, double *info_dev)
+{
+    if (!e) return fail(D2D_EINVAL, "handle is NULL");
+    e->p.obs64 = obs64_dev;
+    e->p.info = info_dev;
+    return D2D_OK;
+}
+
+int d2d_reset(d2d_env *e, const uint8_t *mask_dev, float *obs_dev, void *stream)
+{
+    if (!e) return fail(D2D_EINVAL, "handle is NULL");
+    if (!e->tables_set) return fail(D2D_ESTATE, "test mode: call d2d_set_scenario before d2d_reset");
+    DeviceGuard guard(e->device);
+    D2dParams p = e->p;
+    p.mask = mask_dev; p.obs = obs_dev;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int grid = grid_for(p.n, D2D_BLOCK);
+    if (e->cfg.mode == D2D_MODE_CURRICULUM) d2d_reset_kernel<true><<<grid, D2D_BLOCK, 0, st>>>(p);
+    else d2d_reset_kernel<false><<<grid, D2D_BLOCK, 0, st>>>(p);
+    e->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return D2D_OK;
+}
+
+int d2d_step(d2d_env *e, const float *actions_dev, float *obs_dev, float *reward_dev, uint8_t *done_dev,
+             float *terminal_obs_dev, int auto_reset, void *stream)
+{
+    if (!e) return fail(D2D_EINVAL, "handle is NULL");
+    if (!e->tables_set) return fail(D2D_ESTATE, "test mode: call d2d_set_scenario before d2d_step");
+    if (!obs_dev || !reward_dev || !done_dev) return fail(D2D_EINVAL, "obs/reward/done must be non-NULL");
+    DeviceGuard guard(e->device);
+    D2dParams p = e->p;
+    p.actions = actions_dev; p.obs = obs_dev; p.reward = reward_dev; p.done = done_dev;
+    p.terminal_obs = terminal_obs_dev; p.auto_reset = auto_reset; p.step_index = e->step_index++;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int grid = grid_for(p.n, D2D_BLOCK);
+    if (e->cfg.mode == D2D_MODE_CURRICULUM) d2d_step_kernel<true><<<grid, D2D_BLOCK, 0, st>>>(p);
+    else d2d_step_kernel<false><<<grid, D2D_BLOCK, 0, st>>>(p);
+    e->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return D2D_OK;
+}
+
+int d2d_step_host(d2d_env *e, const float *actions_host, float *obs_host, float *reward_host, uint8_t *done_host,
+                  int auto_reset, void *stream)
+{
+    if (!e) return fail(D2D_EINVAL, "handle is NULL");
+    if (!obs_host || !reward_host || !done_host) return fail(D2D_EINVAL, "obs/reward/done must be non-NULL");
+    DeviceGuard guard(e->device);
+    const int64_t n = e->lay.n;
+    const size_t b_act = n * 2 * sizeof(float), b_obs = n * D2D_OBS_DIM * sizeof(float), b_rew = n * sizeof(float);
+    if (!e->d_obs) {
+        CUDA_TRY(cudaMalloc(&e->d_act, b_act)); CUDA_TRY(cudaMalloc(&e->d_obs, b_obs));
+        CUDA_TRY(cudaMalloc(&e->d_rew, b_rew)); CUDA_TRY(cudaMalloc(&e->d_done, n));
+        CUDA_TRY(cudaHostAlloc(&e->h_act, b_act, cudaHostAllocDefault)); CUDA_TRY(cudaHostAlloc(&e->h_obs, b_obs, cudaHostAllocDefault));
+        CUDA_TRY(cudaHostAlloc(&e->h_rew, b_rew, cudaHostAllocDefault)); CUDA_TRY(cudaHostAlloc(&e->h_done, n, cudaHostAllocDefault));
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const float *dact = nullptr;
+    if (actions_host) {
+        memcpy(e->h_act, actions_host, b_act);
+        CUDA_TRY(cudaMemcpyAsync(e->d_act, e->h_act, b_act, cudaMemcpyHostToDevice, st));
+        dact = e->d_act;
+    }
+    int rc = d2d_step(e, dact, e->d_obs, e->d_rew, e->d_done, nullptr, auto_reset, stream);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(e->h_obs, e->d_obs, b_obs, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(e->h_rew, e->d_rew, b_rew, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(e->h_done, e->d_done, n, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    memcpy(obs_host, e->h_obs, b_obs); memcpy(reward_host, e->h_rew, b_rew); memcpy(done_host, e->h_done, n);
+    return D2D_OK;
+}
+
+static int state_transfer(d2d_env *e, double *host, int to_host)
+{
+    if (!e || !host) return fail(D2D_EINVAL, "NULL argument");
+    DeviceGuard guard(e->device);
+    const int64_t n = e->lay.n;
+    const size_t bytes = n * D2D_STATE_DOUBLES * sizeof(double);
+    double *blob = nullptr;
+    CUDA_TRY(cudaMalloc(&blob, bytes));
+    cudaError_t err = cudaSuccess;
+    if (!to_host) err = cudaMemcpy(blob, host, bytes, cudaMemcpyHostToDevice);
+    if (!err) {
+        d2d_pack_state_kernel<<<grid_for(n, 128), 128>>>(e->p, blob, to_host);
+        e->launches++;
+        err = cudaGetLastError();
+        if (!err) err = cudaDeviceSynchronize();
+    }
+    if (!err && to_host) err = cudaMemcpy(host, blob, bytes, cudaMemcpyDeviceToHost);
+    cudaFree(blob);
+    if (err) return fail(D2D_ECUDA, "state transfer: %s", cudaGetErrorString(err));
+    return D2D_OK;
+}
+
+int d2d_get_state(d2d_env *e, double *state_host) { return state_transfer(e, state_host, 1); }
+int d2d_set_state(d2d_env *e, const double *state_host) { return state_transfer(e, (double *)state_host, 0); }
+
+int d2d_episode_stats(d2d_env *e, double *stats_host, int reset_after)
+{
+    if (!e || !stats_host) return fail(D2D_EINVAL, "NULL argument");
+    DeviceGuard guard(e->device);
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaMemcpy(stats_host, e->stats_dev, D2D_STATS_DOUBLES * sizeof(double), cudaMemcpyDeviceToHost));
+    stats_host[14] = (double)e->step_index * (double)e->lay.n;
+    if (reset_after) CUDA_TRY(cudaMemset(e->stats_dev, 0, D2D_STATS_DOUBLES * sizeof(double)));
+    return D2D_OK;
+}
+
+int d2d_episode_stats_dev(d2d_env *e, double **stats_dev)
+{
+    if (!e || !stats_dev) return fail(D2D_EINVAL, "NULL argument");
+    *stats_dev = e->stats_dev;
+    return D2D_OK;
+}
+
+int d2d_debug_closest_u(d2d_env *e, const double *pos_dev, double *u_dev, int32_t *nfev_dev, void *stream)
+{
+    if (!e || !pos_dev || !u_dev || !nfev_dev) return fail(D2D_EINVAL, "NULL argument");
+    if (!e->tables_set) return fail(D2D_ESTATE, "tables not set");
+    DeviceGuard guard(e->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int grid = grid_for(e->p.n, 128);
+    if (e->cfg.mode == D2D_MODE_CURRICULUM) d2d_closest_u_kernel<true><<<grid, 128, 0, st>>>(e->p, pos_dev, u_dev, nfev_dev);
+    else d2d_closest_u_kernel<false><<<grid, 128, 0, st>>>(e->p, pos_dev, u_dev, nfev_dev);
+    e->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return D2D_OK;
+}
+
+int64_t d2d_launch_count(const d2d_env *e) { return e ? e->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,838 @@
+// drone2d_device.cuh -- device functions of the fused Drone2dEnv step (sm_100a).
+//
+// One lane = one environment; all arithmetic is float64 (the reference is
+// float64 end to end and a float32 solver drifts 1e-1 px in 200 steps).
+// File:line citations are relative to the reference's drone_2d_custom_gym_env/
+// ("env" = drone_2d_env.py); Chipmunk/scipy behaviour is restated in
+// SURVEY.md Appendix A.
+//
+// Two arithmetic regimes:
+//   * "strict" helpers (S::mul/add/...) map to the round-to-nearest intrinsics,
+//     which nvcc never contracts into FMAs.  The closest-point search (Brent on
+//     a flat-bottomed objective) and the nearest-obstacle ranking are
+//     discontinuous functions of their inputs, so they are evaluated with the
+//     reference's exact operation order: identical inputs give bit-identical
+//     u*, evaluation counts and obstacle indices.
+//   * everything else (rigid-body solver, normalisation, reward) is ordinary
+//     double arithmetic with FMA contraction; it differs from the reference by
+//     rounding only (parity tolerance in tests/).
+#pragma once
+#include <cuda_runtime.h>
+#include <math_constants.h>
+
+#include "drone2d_layout.h"
+
+#define D2D_PI 3.14159265358979323846
+#define D2D_TWO_PI 6.28318530717958647692
+
+namespace d2d {
+
+struct S {  // strict IEEE double ops, never contracted
+    static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+    static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+    static __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
+    static __device__ __forceinline__ double div(double a, double b) { return __ddiv_rn(a, b); }
+    static __device__ __forceinline__ double fma(double a, double b, double c) { return __fma_rn(a, b, c); }
+    static __device__ __forceinline__ double sqrt(double a) { return __dsqrt_rn(a); }
+};
+
+// ---------------------------------------------------------------------------
+// scalar helpers
+// ---------------------------------------------------------------------------
+
+// Exact fmod(a, b) for b > 0 and |a/b| < 2^20: the remainder of an IEEE fmod is
+// always representable, so one FMA recovers it once the quotient is right.
+__device__ __forceinline__ double fmod_small(double a, double b)
+{
+    double q = trunc(a / b);
+    double r = __fma_rn(-q, b, a);
+    // a/b may have rounded across an integer: repair by one period (exact).
+    if (a >= 0.0) {
+        if (r < 0.0) r += b;
+        else if (r >= b) r -= b;
+    } else {
+        if (r > 0.0) r -= b;
+        else if (r <= -b) r += b;
+    }
+    return r;
+}
+
+// Python / numpy float modulo for a positive divisor (result in [0, b)).
+__device__ __forceinline__ double py_mod_pos(double a, double b)
+{
+    double m = fmod_small(a, b);
+    if (m < 0.0) m += b;
+    return m;   // m == -0.0 cannot survive: (-0.0 < 0) is false, numpy returns +0.0 via copysign; harmless
+}
+
+// transformations.py:6-7
+__device__ __forceinline__ double ssa(double a) { return py_mod_pos(a + D2D_PI, D2D_TWO_PI) - D2D_PI; }
+
+// env:972-978
+__device__ __forceinline__ double m1to1(double v, double lo, double hi) { return 2.0 * (v - lo) / (hi - lo) - 1.0; }
+__device__ __forceinline__ double invm1to1(double v, double lo, double hi) { return (v + 1.0) * (hi - lo) / 2.0 + lo; }
+__device__ __forceinline__ double clipd(double v, double lo, double hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+// ---------------------------------------------------------------------------
+// Philox4x32-10 counter-based stream (reset sampling, random actions)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                              uint32_t k0, uint32_t k1, uint32_t out[4])
+{
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+        uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+        uint32_t n0 = h1 ^ c1 ^ k0, n2 = h0 ^ c3 ^ k1;
+        c0 = n0; c1 = l1; c2 = n2; c3 = l0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+#define D2D_STREAM_RESET 0x52534554u   // 'RSET'
+#define D2D_STREAM_ACTION 0x4143544Eu  // 'ACTN'
+
+__device__ __forceinline__ double u01_from_bits(uint32_t hi, uint32_t lo)
+{
+    // 53-bit uniform in [0,1) (numpy's random_double construction)
+    return ((double)(hi >> 5) * 67108864.0 + (double)(lo >> 6)) * (1.0 / 9007199254740992.0);
+}
+
+// Sequential draws d = 0,1,2,... of one (env, episode): block d/2 of the stream.
+struct ResetRng {
+    uint32_t env, episode, k0, k1, blk;
+    double spare;
+    bool has;
+    __device__ ResetRng(uint32_t env_, uint32_t ep_, uint32_t k0_, uint32_t k1_)
+        : env(env_), episode(ep_), k0(k0_), k1(k1_), blk(0), spare(0.0), has(false) {}
+    __device__ double u01()
+    {
+        if (has) { has = false; return spare; }
+        uint32_t o[4];
+        philox4x32_10(env, episode, blk, D2D_STREAM_RESET, k0, k1, o);
+        blk++;
+        spare = u01_from_bits(o[2], o[3]);
+        has = true;
+        return u01_from_bits(o[0], o[1]);
+    }
+    __device__ double uniform(double lo, double hi) { return lo + (hi - lo) * u01(); }
+    // Box-Muller (cosine branch), consumes two draws
+    __device__ double normal(double mu, double sd)
+    {
+        double u1 = u01(), u2 = u01();
+        double z = sqrt(-2.0 * log(1.0 - u1)) * cos(D2D_TWO_PI * u2);
+        return mu + sd * z;
+    }
+    __device__ int randint(int a, int b)   // inclusive, like random.randint
+    {
+        int v = a + (int)floor(u01() * (double)(b - a + 1));
+        return v > b ? b : v;
+    }
+};
+
+// ---------------------------------------------------------------------------
+// table views: shared scenario (smem) or per-env rows (global, row-major by index)
+// ---------------------------------------------------------------------------
+struct SharedView {
+    const D2dSharedTables *t;
+    __device__ __forceinline__ int n_wps() const { return t->n_wps; }
+    __device__ __forceinline__ int n_obs() const { return t->n_obs; }
+    __device__ __forceinline__ double us(int k) const { return t->us[k]; }
+    __device__ __forceinline__ double2 wp(int k) const { return make_double2(t->wx[k], t->wy[k]); }
+    __device__ __forceinline__ double2 pa(int r) const { return make_double2(t->ax[r], t->ay[r]); }
+    __device__ __forceinline__ double2 pb(int r) const { return make_double2(t->bx[r], t->by[r]); }
+    __device__ __forceinline__ double2 pc(int r) const { return make_double2(t->cx[r], t->cy[r]); }
+    __device__ __forceinline__ void obstacle(int k, double &x, double &y, double &r) const
+    {
+        x = t->ox[k]; y = t->oy[k]; r = t->orad[k];
+    }
+};
+
+struct EnvView {
+    const D2dParams *p;
+    int64_t i;
+    int nobs;
+    __device__ __forceinline__ int n_wps() const { return p->c.n_wps; }
+    __device__ __forceinline__ int n_obs() const { return nobs; }
+    __device__ __forceinline__ double us(int k) const { return p->us[(int64_t)k * p->np + i]; }
+    __device__ __forceinline__ double2 wp(int k) const { return p->wps[(int64_t)k * p->np + i]; }
+    __device__ __forceinline__ double2 pa(int r) const { return p->pa[(int64_t)r * p->np + i]; }
+    __device__ __forceinline__ double2 pb(int r) const { return p->pb[(int64_t)r * p->np + i]; }
+    __device__ __forceinline__ double2 pc(int r) const { return p->pc[(int64_t)r * p->np + i]; }
+    __device__ __forceinline__ void obstacle(int k, double &x, double &y, double &r) const
+    {
+        double2 xy = p->obxy[(int64_t)k * p->np + i];
+        x = xy.x; y = xy.y; r = p->obr[(int64_t)k * p->np + i];
+    }
+};
+
+// ---------------------------------------------------------------------------
+// QPMI2D (predef_path.py:53-188), strict arithmetic
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double poly2(double a, double b, double c, double u, double uu)
+{
+    return S::add(S::add(S::mul(a, uu), S::mul(b, u)), c);   // a*u**2 + b*u + c
+}
+
+template <class V>
+__device__ __forceinline__ int u_index(const V &v, double u, int N)
+{
+    // predef_path.py:53-63: first n with u <= us[n+1]; us ascending -> count of us[k] < u
+    int n = 0;
+    for (int k = 1; k < N; k++) n += (u > v.us(k)) ? 1 : 0;
+    return n;
+}
+
+// predef_path.py:88-142
+template <class V>
+__device__ __forceinline__ void path_eval(const V &v, double u, double &x, double &y)
+{
+    const int N = v.n_wps(), rows = N - 2;
+    const double uu = S::mul(u, u);
+    int r;
+    if (u >= v.us(0) && u <= v.us(1)) {
+        r = 0;
+    } else if (u >= S::sub(v.us(N - 2), 0.001)) {
+        // (us[-2]-0.001 <= u <= us[-1]) or get_u_index(u) == len(us)-1 (i.e. u > us[-1])
+        r = rows - 1;
+    } else {
+        const int n = u_index(v, u, N);
+        const double un = v.us(n), un1 = v.us(n + 1);
+        const double len = S::sub(un1, un);
+        const double mu_r = S::div(S::sub(u, un), len);
+        const double mu_f = S::div(S::sub(un1, u), len);
+        const int r1 = (n - 1 < 0) ? rows - 1 : n - 1;       // Python negative index for u < 0
+        const double2 a1 = v.pa(r1), b1 = v.pb(r1), c1 = v.pc(r1);
+        const double2 a2 = v.pa(n), b2 = v.pb(n), c2 = v.pc(n);
+        const double x1 = poly2(a1.x, b1.x, c1.x, u, uu), y1 = poly2(a1.y, b1.y, c1.y, u, uu);
+        const double x2 = poly2(a2.x, b2.x, c2.x, u, uu), y2 = poly2(a2.y, b2.y, c2.y, u, uu);
+        x = S::add(S::mul(mu_r, x2), S::mul(mu_f, x1));
+        y = S::add(S::mul(mu_r, y2), S::mul(mu_f, y1));
+        return;
+    }
+    const double2 a = v.pa(r), b = v.pb(r), c = v.pc(r);
+    x = poly2(a.x, b.x, c.x, u, uu);
+    y = poly2(a.y, b.y, c.y, u, uu);
+}
+
+// predef_path.py:145-188 (only used by the obstacle sampler of the reset)
+template <class V>
+__device__ __forceinline__ void path_gradient(const V &v, double u, double &dx, double &dy)
+{
+    const int N = v.n_wps(), rows = N - 2;
+    int r;
+    if (u >= v.us(0) && u <= v.us(1)) {
+        r = 0;
+    } else if (u >= v.us(N - 2)) {
+        r = rows - 1;
+    } else {
+        const int n = u_index(v, u, N);
+        const double un = v.us(n), un1 = v.us(n + 1);
+        const double len = S::sub(un1, un);
+        const double mu_r = S::div(S::sub(u, un), len);
+        const double mu_f = S::div(S::sub(un1, u), len);
+        const int r1 = (n - 1 < 0) ? rows - 1 : n - 1;
+        const double2 a1 = v.pa(r1), b1 = v.pb(r1), a2 = v.pa(n), b2 = v.pb(n);
+        const double dx1 = S::add(S::mul(S::mul(a1.x, u), 2.0), b1.x), dy1 = S::add(S::mul(S::mul(a1.y, u), 2.0), b1.y);
+        const double dx2 = S::add(S::mul(S::mul(a2.x, u), 2.0), b2.x), dy2 = S::add(S::mul(S::mul(a2.y, u), 2.0), b2.y);
+        dx = S::add(S::mul(mu_r, dx2), S::mul(mu_f, dx1));
+        dy = S::add(S::mul(mu_r, dy2), S::mul(mu_f, dy1));
+        return;
+    }
+    const double2 a = v.pa(r), b = v.pb(r);
+    dx = S::add(S::mul(S::mul(a.x, u), 2.0), b.x);
+    dy = S::add(S::mul(S::mul(a.y, u), 2.0), b.y);
+}
+
+// np.linalg.norm(path(u) - pos) (predef_path.py:246): sqrt(x.dot(x)) with BLAS
+// ddot's fused accumulate -> sqrt(fma(dy, dy, dx*dx)).
+template <class V>
+__device__ __forceinline__ double path_dist(const V &v, double u, double px, double py)
+{
+    double x, y;
+    path_eval(v, u, x, y);
+    const double dx = S::sub(x, px), dy = S::sub(y, py);
+    return S::sqrt(S::fma(dy, dy, S::mul(dx, dx)));
+}
+
+// QPMI2D.get_closest_u (predef_path.py:226-248) = scipy fminbound = bounded Brent
+// (_minimize_scalar_bounded, scipy/optimize/_optimize.py:2289-2440) on
+// [-10, L+10], xatol = 1e-6, maxfun = 500.  Literal restatement; every lane runs
+// its own iteration count (mean ~15, max ~47).
+template <class V>
+__device__ double closest_u(const V &v, double px, double py, int &nfev)
+{
+    const double xatol = 1e-6;
+    const int maxfun = 500;
+    const double sqrt_eps = 1.4832396974191326e-08;      // sqrt(2.2e-16)
+    const double golden_mean = 0.3819660112501051;        // 0.5*(3 - sqrt(5))
+    double a = -10.0, b = S::add(v.us(v.n_wps() - 1), 10.0);
+    double fulc = S::add(a, S::mul(golden_mean, S::sub(b, a)));
+    double nfc = fulc, xf = fulc;
+    double rat = 0.0, e = 0.0;
+    double x = xf;
+    double fx = path_dist(v, x, px, py);
+    int num = 1;
+    double fu;
+    double ffulc = fx, fnfc = fx;
+    double xm = S::mul(0.5, S::add(a, b));
+    double tol1 = S::add(S::mul(sqrt_eps, fabs(xf)), xatol / 3.0);
+    double tol2 = S::mul(2.0, tol1);
+
+    while (fabs(S::sub(xf, xm)) > S::sub(tol2, S::mul(0.5, S::sub(b, a)))) {
+        bool golden = true;
+        if (fabs(e) > tol1) {
+            golden = false;
+            double r = S::mul(S::sub(xf, nfc), S::sub(fx, ffulc));
+            double q = S::mul(S::sub(xf, fulc), S::sub(fx, fnfc));
+            double p = S::sub(S::mul(S::sub(xf, fulc), q), S::mul(S::sub(xf, nfc), r));
+            q = S::mul(2.0, S::sub(q, r));
+            if (q > 0.0) p = -p;
+            q = fabs(q);
+            r = e;
+            e = rat;
+            if ((fabs(p) < fabs(S::mul(S::mul(0.5, q), r))) && (p > S::mul(q, S::sub(a, xf))) &&
+                (p < S::mul(q, S::sub(b, xf)))) {
+                rat = S::div(S::add(p, 0.0), q);
+                x = S::add(xf, rat);
+                if ((S::sub(x, a) < tol2) || (S::sub(b, x) < tol2)) {
+                    const double d = S::sub(xm, xf);
+                    const double si = (double)((d > 0.0) - (d < 0.0)) + (d == 0.0 ? 1.0 : 0.0);
+                    rat = S::mul(tol1, si);
+                }
+            } else {
+                golden = true;
+            }
+        }
+        if (golden) {
+            e = (xf >= xm) ? S::sub(a, xf) : S::sub(b, xf);
+            rat = S::mul(golden_mean, e);
+        }
+        const double si = (double)((rat > 0.0) - (rat < 0.0)) + (rat == 0.0 ? 1.0 : 0.0);
+        x = S::add(xf, S::mul(si, fmax(fabs(rat), tol1)));
+        fu = path_dist(v, x, px, py);
+        num += 1;
+
+        if (fu <= fx) {
+            if (x >= xf) a = xf; else b = xf;
+            fulc = nfc; ffulc = fnfc;
+            nfc = xf; fnfc = fx;
+            xf = x; fx = fu;
+        } else {
+            if (x < xf) a = x; else b = x;
+            if ((fu <= fnfc) || (nfc == xf)) {
+                fulc = nfc; ffulc = fnfc;
+                nfc = x; fnfc = fu;
+            } else if ((fu <= ffulc) || (fulc == xf) || (fulc == nfc)) {
+                fulc = x; ffulc = fu;
+            }
+        }
+        xm = S::mul(0.5, S::add(a, b));
+        tol1 = S::add(S::mul(sqrt_eps, fabs(xf)), xatol / 3.0);
+        tol2 = S::mul(2.0, tol1);
+        if (num >= maxfun) break;
+    }
+    nfev = num;
+    return xf;
+}
+
+// ---------------------------------------------------------------------------
+// per-env dynamic state held in registers for the duration of a step
+// ---------------------------------------------------------------------------
+struct EnvState {
+    double px[3], py[3], vx[3], vy[3], an[3], om[3];
+    double jx[6], jy[6];
+    double path_error, total_reward;
+    int steps, flags, episode, n_obs;
+};
+
+__device__ __forceinline__ void load_state(const D2dParams &p, int64_t i, EnvState &s)
+{
+#pragma unroll
+    for (int b = 0; b < 3; b++) {
+        const double2 P = p.pos[b * p.np + i], V = p.vel[b * p.np + i], A = p.ang[b * p.np + i];
+        s.px[b] = P.x; s.py[b] = P.y; s.vx[b] = V.x; s.vy[b] = V.y; s.an[b] = A.x; s.om[b] = A.y;
+    }
+#pragma unroll
+    for (int j = 0; j < 6; j++) {
+        const double2 J = p.jacc[j * p.np + i];
+        s.jx[j] = J.x; s.jy[j] = J.y;
+    }
+    const double2 A = p.acc[i];
+    s.path_error = A.x; s.total_reward = A.y;
+    const int4 m = p.meta[i];
+    s.steps = m.x; s.flags = m.y; s.episode = m.z; s.n_obs = m.w;
+}
+
+__device__ __forceinline__ void store_state(const D2dParams &p, int64_t i, const EnvState &s)
+{
+#pragma unroll
+    for (int b = 0; b < 3; b++) {
+        p.pos[b * p.np + i] = make_double2(s.px[b], s.py[b]);
+        p.vel[b * p.np + i] = make_double2(s.vx[b], s.vy[b]);
+        p.ang[b * p.np + i] = make_double2(s.an[b], s.om[b]);
+    }
+#pragma unroll
+    for (int j = 0; j < 6; j++) p.jacc[j * p.np + i] = make_double2(s.jx[j], s.jy[j]);
+    p.acc[i] = make_double2(s.path_error, s.total_reward);
+    p.meta[i] = make_int4(s.steps, s.flags, s.episode, s.n_obs);
+}
+
+// Drone.__init__ (Drone.py:9-95): three bodies at rest, impulses cleared.
+__device__ __forceinline__ void spawn(EnvState &s, const D2dConst &c, double x, double y, double angle)
+{
+    double sn, cs, sn2, cs2;
+    sincos(angle, &sn, &cs);
+    sincos(angle + D2D_PI, &sn2, &cs2);
+    s.px[0] = x; s.py[0] = y;
+    s.px[1] = cs2 * c.R + x; s.py[1] = sn2 * c.R + y;     // Drone.py:37
+    s.px[2] = cs * c.R + x; s.py[2] = sn * c.R + y;       // Drone.py:51
+#pragma unroll
+    for (int b = 0; b < 3; b++) { s.vx[b] = 0.0; s.vy[b] = 0.0; s.an[b] = angle; s.om[b] = 0.0; }
+#pragma unroll
+    for (int j = 0; j < 6; j++) { s.jx[j] = 0.0; s.jy[j] = 0.0; }
+    s.path_error = 0.0; s.total_reward = 0.0;
+    s.steps = 0;
+    s.flags = D2D_F_INIT;
+}
+
+// ---------------------------------------------------------------------------
+// thrust + cpSpaceStep (env:400-406).  Returns the frame's
+// new rotation (cos, sin) for the collision test / observation.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void physics_step(EnvState &s, const D2dConst &c, double act_l, double act_r,
+                                             double &rc0, double &rs0)
+{
+    const double dt = c.dt;
+    // env:400-401 (float64 arithmetic on the float32 action, numpy 1.x promotion)
+    const double FL = (act_l / 2.0 + 0.5) * c.force_scale;
+    const double FR = (act_r / 2.0 + 0.5) * c.force_scale;
+
+    // cpBodyApplyForceAtLocalPoint on the frame, transform of the CURRENT pose
+    double fx, fy, tq;
+    {
+        double ry, rx;
+        sincos(s.an[0], &ry, &rx);
+        const double fwxL = -ry * FL, fwyL = rx * FL, fwxR = -ry * FR, fwyR = rx * FR;
+        const double rLx = (rx * -c.R + s.px[0]) - s.px[0], rLy = (ry * -c.R + s.py[0]) - s.py[0];
+        const double rRx = (rx * c.R + s.px[0]) - s.px[0], rRy = (ry * c.R + s.py[0]) - s.py[0];
+        fx = fwxL + fwxR; fy = fwyL + fwyR;
+        tq = (rLx * fwyL - rLy * fwxL) + (rRx * fwyR - rRy * fwxR);
+    }
+
+    // 1. cpBodyUpdatePosition
+    double rc[3], rs[3];
+#pragma unroll
+    for (int b = 0; b < 3; b++) {
+        s.px[b] = s.px[b] + s.vx[b] * dt;
+        s.py[b] = s.py[b] + s.vy[b] * dt;
+        s.an[b] = s.an[b] + s.om[b] * dt;
+        sincos(s.an[b], &rs[b], &rc[b]);
+    }
+    rc0 = rc[0]; rs0 = rs[0];
+
+    // 4. cpPivotJoint preStep.  Anchors lie on the body x axis, so
+    //    r1 = Rot(a_motor) * (ax, 0) = (c*ax, s*ax) and r2 = (c0*bx, s0*bx).
+    double r1x[6], r1y[6], r2x[6], r2y[6], k11[6], k12[6], k22[6], bsx[6], bsy[6];
+#pragma unroll
+    for (int j = 0; j < 6; j++) {
+        const int m = (j < 3) ? 1 : 2;
+        const double ax = (double)((j % 3) - 1) * c.d;                        // -d, 0, +d (Drone.py:61-95)
+        const double bx = ((j < 3) ? -c.R : c.R) + ax;
+        r1x[j] = rc[m] * ax; r1y[j] = rs[m] * ax;
+        r2x[j] = rc[0] * bx; r2y[j] = rs[0] * bx;
+        // k_tensor(a = motor, b = frame)
+        double a11 = c.msum, a12 = 0.0, a22 = c.msum;
+        a11 += r1y[j] * r1y[j] * c.iinv_m; a12 += -r1x[j] * r1y[j] * c.iinv_m; a22 += r1x[j] * r1x[j] * c.iinv_m;
+        a11 += r2y[j] * r2y[j] * c.iinv_f; a12 += -r2x[j] * r2y[j] * c.iinv_f; a22 += r2x[j] * r2x[j] * c.iinv_f;
+        const double det_inv = 1.0 / (a11 * a22 - a12 * a12);
+        k11[j] = a22 * det_inv; k12[j] = -a12 * det_inv; k22[j] = a11 * det_inv;
+        // bias = -delta / dt (error_bias = 0 -> bias_coef = 1)
+        bsx[j] = ((s.px[0] + r2x[j]) - (s.px[m] + r1x[j])) * c.bias_coef;
+        bsy[j] = ((s.py[0] + r2y[j]) - (s.py[m] + r1y[j])) * c.bias_coef;
+    }
+
+    // 5. cpBodyUpdateVelocity (space damping 1; env:376-380 has no physical effect)
+    s.vx[0] = s.vx[0] + (c.gx + fx * c.minv_f) * dt;
+    s.vy[0] = s.vy[0] + (c.gy + fy * c.minv_f) * dt;
+    s.om[0] = s.om[0] + tq * c.iinv_f * dt;
+#pragma unroll
+    for (int b = 1; b < 3; b++) {
+        s.vx[b] = s.vx[b] + c.gx * dt;
+        s.vy[b] = s.vy[b] + c.gy * dt;
+    }
+
+    // 6. warm start with the cached impulses (dt_coef = 1; all zero on the first step)
+#pragma unroll
+    for (int j = 0; j < 6; j++) {
+        const int m = (j < 3) ? 1 : 2;
+        const double jx = s.jx[j], jy = s.jy[j];
+        s.vx[m] -= jx * c.minv_m; s.vy[m] -= jy * c.minv_m;
+        s.om[m] -= c.iinv_m * (r1x[j] * jy - r1y[j] * jx);
+        s.vx[0] += jx * c.minv_f; s.vy[0] += jy * c.minv_f;
+        s.om[0] += c.iinv_f * (r2x[j] * jy - r2y[j] * jx);
+    }
+
+    // 7. sequential impulses: iterations x 6 joints, Gauss-Seidel order left_1..right_3
+#pragma unroll 1
+    for (int it = 0; it < c.iterations; it++) {
+#pragma unroll
+        for (int j = 0; j < 6; j++) {
+            const int m = (j < 3) ? 1 : 2;
+            const double vrx = (s.vx[0] - r2y[j] * s.om[0]) - (s.vx[m] - r1y[j] * s.om[m]);
+            const double vry = (s.vy[0] + r2x[j] * s.om[0]) - (s.vy[m] + r1x[j] * s.om[m]);
+            const double ex = bsx[j] - vrx, ey = bsy[j] - vry;
+            double jx = ex * k11[j] + ey * k12[j];
+            double jy = ex * k12[j] + ey * k22[j];
+            const double ox = s.jx[j], oy = s.jy[j];
+            s.jx[j] = ox + jx; s.jy[j] = oy + jy;          // clamp to maxForce*dt = inf is a no-op
+            jx = s.jx[j] - ox; jy = s.jy[j] - oy;
+            s.vx[m] -= jx * c.minv_m; s.vy[m] -= jy * c.minv_m;
+            s.om[m] -= c.iinv_m * (r1x[j] * jy - r1y[j] * jx);
+            s.vx[0] += jx * c.minv_f; s.vy[0] += jy * c.minv_f;
+            s.om[0] += c.iinv_f * (r2x[j] * jy - r2y[j] * jx);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// one pass over the obstacles: sensor overlap of the rotated frame box
+//  and the reference's nearest-k ranking (env:617-629,
+// 948-961: min over the 4 UNROTATED box corners of |corner - centre| - r,
+// stable ascending order).
+// ---------------------------------------------------------------------------
+struct Nearest {
+    double d[3];
+    int idx[3];
+    double ox[3], oy[3];
+};
+
+template <class V>
+__device__ __forceinline__ bool scan_obstacles(const V &v, const D2dConst &c, double x, double y,
+                                               double rc0, double rs0, bool test_collision, Nearest &nr)
+{
+    bool hit = false;
+#pragma unroll
+    for (int k = 0; k < 3; k++) { nr.d[k] = CUDART_INF; nr.idx[k] = -1; nr.ox[k] = 0.0; nr.oy[k] = 0.0; }
+    const int n = v.n_obs();
+    // corners of the unrotated box: (+-hw + x, +-hh + y)   (v1 + body.position, env:955)
+    const double cxp = S::add(c.hw, x), cxm = S::add(-c.hw, x);
+    const double cyp = S::add(c.hh, y), cym = S::add(-c.hh, y);
+    for (int k = 0; k < n; k++) {
+        double ox, oy, orad;
+        v.obstacle(k, ox, oy, orad);
+        if (test_collision) {
+            const double dx = ox - x, dy = oy - y;
+            const double qx = rc0 * dx + rs0 * dy, qy = rc0 * dy - rs0 * dx;
+            const double ex = fmax(fabs(qx) - c.hw, 0.0), ey = fmax(fabs(qy) - c.hh, 0.0);
+            hit = hit || (sqrt(ex * ex + ey * ey) <= orad);
+        }
+        // min over corners of sqrt(dx^2+dy^2) - r: the rounded operations are monotone,
+        // so the minimum separates per axis and one sqrt suffices (bit-identical).
+        const double dxp = S::sub(cxp, ox), dxm = S::sub(cxm, ox);
+        const double dyp = S::sub(cyp, oy), dym = S::sub(cym, oy);
+        const double qx2 = fmin(S::mul(dxp, dxp), S::mul(dxm, dxm));
+        const double qy2 = fmin(S::mul(dyp, dyp), S::mul(dym, dym));
+        const double dist = S::sub(S::sqrt(S::add(qx2, qy2)), orad);
+        // stable insertion (strict <: ties keep the lower index first, like sorted())
+        if (dist < nr.d[2]) {
+            if (dist < nr.d[1]) {
+                nr.d[2] = nr.d[1]; nr.idx[2] = nr.idx[1]; nr.ox[2] = nr.ox[1]; nr.oy[2] = nr.oy[1];
+                if (dist < nr.d[0]) {
+                    nr.d[1] = nr.d[0]; nr.idx[1] = nr.idx[0]; nr.ox[1] = nr.ox[0]; nr.oy[1] = nr.oy[0];
+                    nr.d[0] = dist; nr.idx[0] = k; nr.ox[0] = ox; nr.oy[0] = oy;
+                } else {
+                    nr.d[1] = dist; nr.idx[1] = k; nr.ox[1] = ox; nr.oy[1] = oy;
+                }
+            } else {
+                nr.d[2] = dist; nr.idx[2] = k; nr.ox[2] = ox; nr.oy[2] = oy;
+            }
+        }
+    }
+    return hit;
+}
+
+// ---------------------------------------------------------------------------
+// observation (env:631-773).  Writes the 27 values through `put(j, value)` and
+// returns the float64 quantities the reward needs.
+// ---------------------------------------------------------------------------
+struct ObsAux {
+    double o0, o1, o3, o4, o5, o6, o7, o8, o9, o10, o17, o18, o19, o20, o23, o24;
+    double u_star;
+    int nfev;
+    int near_packed;
+};
+
+template <class V, class Put>
+__device__ __forceinline__ void observe(const V &v, const D2dConst &c, EnvState &s, double rc0, double rs0,
+                                        const Nearest &nr, Put put, ObsAux &ax)
+{
+    const double W = c.W, H = c.H;
+    const double x = s.px[0], y = s.py[0], alpha = s.an[0];
+    const double2 tgt = v.wp(v.n_wps() - 1);                     // env:316-317
+    ax.o0 = m1to1(s.vx[0], -1330.0, 1330.0); put(0, ax.o0);      // env:633-636
+    ax.o1 = m1to1(s.vy[0], -1330.0, 1330.0); put(1, ax.o1);
+    put(2, clipd(s.om[0] / 11.7, -1.0, 1.0));                    // env:639-640
+    ax.o3 = alpha / D2D_PI; put(3, ax.o3);                       // env:643-644
+    ax.o4 = m1to1(tgt.x - x, 0.0, W); put(4, ax.o4);             // env:648-649
+    ax.o5 = m1to1(tgt.y - y, 0.0, H); put(5, ax.o5);
+    ax.o6 = m1to1(x, 0.0, W); put(6, ax.o6);                     // env:655-656
+    ax.o7 = m1to1(y, 0.0, H); put(7, ax.o7);
+
+    // env:660-720: k nearest obstacles, missing slots = (1, 0, 0)
+    ax.o8 = 1.0; ax.o9 = 0.0; ax.o10 = 0.0;
+    ax.near_packed = 0;
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+        double dn = 1.0, sa = 0.0, ca = 0.0;
+        if (nr.idx[j] >= 0) {
+            double ang = atan2(y - nr.oy[j], x - nr.ox[j]);
+            ang = ssa(ang - alpha - D2D_PI);
+            dn = m1to1(nr.d[j], 0.0, c.diag);
+            sincos(ang, &sa, &ca);
+        }
+        put(8 + 3 * j, dn); put(9 + 3 * j, sa); put(10 + 3 * j, ca);
+        if (j == 0) { ax.o8 = dn; ax.o9 = sa; ax.o10 = ca; }
+        ax.near_packed |= ((nr.idx[j] < 0 ? 255 : nr.idx[j]) & 255) << (8 * j);
+    }
+
+    // env:723-727
+    {
+        const double va = ssa(atan2(s.vy[0], s.vx[0]) - alpha);
+        sincos(va, &ax.o17, &ax.o18);
+        put(17, ax.o17); put(18, ax.o18);
+    }
+
+    // env:730-734.  The reference runs the identical fminbound a second time at
+    // env:737; same arguments -> same result, evaluated once.
+    int nfev;
+    const double u = closest_u(v, x, y, nfev);
+    double cx, cy;
+    path_eval(v, u, cx, cy);
+    ax.o19 = m1to1(cx, 0.0, W); ax.o20 = m1to1(cy, 0.0, H);
+    put(19, ax.o19); put(20, ax.o20);
+    ax.u_star = u; ax.nfev = nfev;
+
+    // env:737-749, predef_path.py:257-266: look-ahead point + permanent latch
+    const double L = v.us(v.n_wps() - 1);
+    const double u_la = (S::add(u, c.lookahead) > L) ? L : S::add(u, c.lookahead);
+    double lx, ly;
+    path_eval(v, u_la, lx, ly);
+    if (fabs(lx - tgt.x) < 10.0 && fabs(ly - tgt.y) < 10.0) s.flags |= D2D_F_LATCHED;
+    if (s.flags & D2D_F_LATCHED) { lx = tgt.x; ly = tgt.y; }
+    put(21, m1to1(lx, 0.0, W)); put(22, m1to1(ly, 0.0, H));
+
+    // env:752-763: R_w_b rotates by +alpha (transformations.py:9-11)
+    {
+        const double dx = lx - x, dy = ly - y;
+        const double ang = ssa(atan2(rs0 * dx + rc0 * dy, rc0 * dx - rs0 * dy) - alpha);
+        sincos(ang, &ax.o23, &ax.o24);
+        put(23, ax.o23); put(24, ax.o24);
+    }
+    {
+        const double dx = cx - x, dy = cy - y;
+        const double ang = ssa(atan2(rs0 * dx + rc0 * dy, rc0 * dx - rs0 * dy) - alpha);
+        double sa, ca;
+        sincos(ang, &sa, &ca);
+        put(25, sa); put(26, ca);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// reward + termination (env:423-613)
+// ---------------------------------------------------------------------------
+struct StepResult {
+    double reward, r_CA, r_PA, r_PP, r_coll, r_end, r_AA, d1, ape;
+    int end_bits;   // 1 collision | 2 reached | 4 time | 8 alpha
+    bool done;
+};
+
+__device__ __forceinline__ void reward_and_done(const D2dConst &c, EnvState &s, const ObsAux &o, bool has_obstacles,
+                                                StepResult &r)
+{
+    const double W = c.W, H = c.H;
+    // env:423-445: decode the observation back to physical units
+    const double vel_x = invm1to1(o.o0, -1330.0, 1330.0), vel_y = invm1to1(o.o1, -1330.0, 1330.0);
+    const double alpha = o.o3 * D2D_PI;
+    const double tdx = invm1to1(o.o4, 0.0, W), tdy = invm1to1(o.o5, 0.0, H);
+    const double pos_x = invm1to1(o.o6, 0.0, W), pos_y = invm1to1(o.o7, 0.0, H);
+    const double vel_angle = py_mod_pos(atan2(o.o17 * D2D_PI, o.o18 * D2D_PI) + D2D_TWO_PI, D2D_TWO_PI);
+    const double cpx = invm1to1(o.o19, 0.0, W), cpy = invm1to1(o.o20, 0.0, H);
+    const double la_angle = py_mod_pos(atan2(o.o23, o.o24) + D2D_TWO_PI, D2D_TWO_PI);
+
+    double lambda_PA = 1.0, lambda_CA = 1.0, r_CA = 0.0, d1 = CUDART_INF;
+    if (has_obstacles) {                                          // env:462-523
+        d1 = invm1to1(o.o8, 0.0, c.diag);
+        const double obs_angle = py_mod_pos(atan2(o.o9, o.o10) + D2D_TWO_PI, D2D_TWO_PI);
+        const double angle_diff =
+            fabs((py_mod_pos(obs_angle - vel_angle + D2D_PI, D2D_TWO_PI) - D2D_PI) * (180.0 / D2D_PI));
+        const double DR = c.danger_range, DA = c.danger_angle, kk = c.k_ca;
+        if (d1 < DR && c.use_Lambda) {
+            lambda_PA = (d1 / DR) / 2.0;
+            if (lambda_PA < 0.10) lambda_PA = 0.10;
+            lambda_CA = 1.0 - lambda_PA;
+        }
+        if (d1 < DR) {
+            double range_rew = -(((DR + kk * DR) / (d1 + kk * DR)) - 1.0);
+            double angle_rew = -(((DA + kk * DA) / (angle_diff + kk * DA)) - 1.0);
+            if (angle_rew > 0.0) angle_rew = 0.0;
+            if (range_rew > 0.0) range_rew = 0.0;
+            r_CA = range_rew + angle_rew;
+        }
+    }
+    // env:527-530
+    const double ddx = cpx - pos_x, ddy = cpy - pos_y;
+    const double dist_from_path = sqrt(fma(ddy, ddy, ddx * ddx));
+    const double r_PA = -(2.0 * (clipd(dist_from_path, 0.0, c.PA_band_edge) / c.PA_band_edge) - 1.0) * c.PA_scale;
+    // env:534-539
+    const double velocity = sqrt(vel_x * vel_x + vel_y * vel_y);
+    const double vel_LA_diff = fabs(py_mod_pos(la_angle - vel_angle + D2D_PI, D2D_TWO_PI) - D2D_PI);
+    const double r_PP = clipd(cos(vel_LA_diff) * (velocity * c.PP_vel_scale), c.PP_rew_min, c.PP_rew_max);
+    // env:543-570
+    int bits = 0;
+    double r_coll = 0.0, r_end = 0.0, r_AA = 0.0;
+    if (s.flags & D2D_F_COLLIDED) { r_coll = c.rew_collision; bits |= 1; }
+    if (fabs(tdx) < c.reach_end_radius && fabs(tdy) < c.reach_end_radius) { r_end = c.rew_reach_end; bits |= 2; }
+    if (alpha > c.AA_band) r_AA = -sin(alpha);
+    if (alpha < -c.AA_band) r_AA = sin(alpha);
+    if (fabs(alpha) >= c.AA_angle) { r_AA = c.rew_AA; bits |= 8; }
+    if (s.steps == c.n_steps) bits |= 4;
+    // env:572
+    r.reward = r_AA + r_PA * lambda_PA + r_PP + r_coll + r_CA * lambda_CA + r_end;
+    r.r_CA = r_CA * lambda_CA; r.r_PA = r_PA * lambda_PA; r.r_PP = r_PP;
+    r.r_coll = r_coll; r.r_end = r_end; r.r_AA = r_AA; r.d1 = d1;
+    s.path_error += dist_from_path;                               // env:589-592
+    r.ape = s.path_error / (double)s.steps;
+    s.total_reward += r.reward;
+    r.end_bits = bits;
+    r.done = (bits != 0) || (s.flags & D2D_F_DONE);
+}
+
+// ---------------------------------------------------------------------------
+// fused re-spawn (env:182-392) from the counter-based stream.  Draw order per
+// (env, episode) -- mirrored by oracle/philox_reset.py:
+//   curriculum: corner, x1, y1, (n_wps-1) azimuths, spawn angle, then per stage
+//               stage_2: x, y | stage_3/4: bernoulli, sampler | stage_5: normal(1,4), samplers
+//   test:       x, y, spawn angle
+//   sampler attempt: u_obs, normal(mean,std) (2 draws), radius
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ int sample_obstacles(const D2dParams &p, EnvView &ev, ResetRng &rng, int slot, int count,
+                                                double mean, double sd, bool on_path)
+{
+    const double L = ev.us(ev.n_wps() - 1);
+    int made = 0, attempts = 0;
+    while (made < count && slot < D2D_MAX_OBS_ENV && attempts < 4096) {   // obstacles.py:63 `while num_obstacles < n`
+        attempts++;
+        const double u_obs = rng.uniform(0.20 * L, 0.90 * L);
+        double gx, gy, x, y;
+        path_gradient(ev, u_obs, gx, gy);
+        const double ang = atan2(gy, gx);
+        const double dist = rng.normal(mean, sd);
+        path_eval(ev, u_obs, x, y);
+        double sn, cs;
+        sincos(ang - D2D_PI / 2, &sn, &cs);
+        const double ox = x + dist * cs, oy = y + dist * sn;
+        const double size = rng.uniform(10.0, 50.0);
+        const double ddx = ox - x, ddy = oy - y;
+        if (on_path) {
+            p.obxy[(int64_t)slot * p.np + ev.i] = make_double2(x, y);
+            p.obr[(int64_t)slot * p.np + ev.i] = size;
+            slot++; made++;
+        } else if (sqrt(ddx * ddx + ddy * ddy) > size + 10.0) {
+            p.obxy[(int64_t)slot * p.np + ev.i] = make_double2(ox, oy);
+            p.obr[(int64_t)slot * p.np + ev.i] = size;
+            slot++; made++;
+        }
+    }
+    return slot;
+}
+
+template <bool PER_ENV>
+__device__ __noinline__ void reset_env(const D2dParams &p, int64_t i, EnvState &s, int episode)
+{
+    const D2dConst &c = p.c;
+    ResetRng rng((uint32_t)(c.env_id_base + i), (uint32_t)episode, c.seed_lo, c.seed_hi);
+    if (!PER_ENV) {
+        // env:221-311: uniform spawn rectangle of the scenario
+        const double x = rng.uniform(c.sp_xmin, c.sp_xmax);
+        const double y = rng.uniform(c.sp_ymin, c.sp_ymax);
+        const double a = rng.uniform(-D2D_PI / 4, D2D_PI / 4);
+        spawn(s, c, x, y, a);
+        s.episode = episode;
+        s.n_obs = 0;
+        return;
+    }
+    // ---- curriculum: random path (predef_path.py:307-363) ----
+    const int N = c.n_wps;
+    int corner = 2;                                              // 'DR' when random_path_spawn is False (env:214)
+    if (c.random_path_spawn) corner = rng.randint(c.corner_lo, c.corner_hi);   // 1 DL, 2 DR, 3 UL, 4 UR (env:202-211)
+    const bool right = (corner == 2 || corner == 4), up = (corner == 3 || corner == 4);
+    double wx = right ? rng.uniform(c.W - 180.0, c.W - 100.0) : rng.uniform(100.0, 180.0);
+    double wy = up ? rng.uniform(c.H - 180.0, c.H - 100.0) : rng.uniform(100.0, 180.0);
+    double az_lo, az_hi;
+    if (corner == 1) { az_lo = 0.0; az_hi = D2D_PI / 2; }
+    else if (corner == 3) { az_lo = 0.0; az_hi = -D2D_PI / 2; }
+    else if (corner == 2) { az_lo = D2D_PI / 2; az_hi = D2D_PI; }
+    else { az_lo = -D2D_PI / 2; az_hi = -D2D_PI; }
+    const double x0 = wx, y0 = wy;
+    // QPMI2D.__init__ (predef_path.py:20-50): chord-length parameter and the
+    // quadratic through each interior waypoint and its neighbours (Newton form;
+    // the reference inverts the 3x3 Vandermonde matrix -- same polynomial).
+    double u_prev2 = 0.0, u_prev = 0.0, u_cur = 0.0;
+    double xa = 0.0, ya = 0.0, xb = wx, yb = wy;                  // waypoints k-2, k-1
+    p.wps[i] = make_double2(wx, wy);
+    p.us[i] = 0.0;
+    for (int k = 1; k < N; k++) {
+        const double az = rng.uniform(az_lo, az_hi);
+        double sn, cs;
+        sincos(az, &sn, &cs);
+        const double nx = xb + c.seg_len * cs, ny = yb + c.seg_len * sn;
+        const double ddx = nx - xb, ddy = ny - yb;
+        u_cur = u_prev + sqrt(ddx * ddx + ddy * ddy);
+        p.wps[(int64_t)k * p.np + i] = make_double2(nx, ny);
+        p.us[(int64_t)k * p.np + i] = u_cur;
+        if (k >= 2) {
+            const double u0 = u_prev2, u1 = u_prev, u2 = u_cur;
+            const double dx01 = (xb - xa) / (u1 - u0), dx12 = (nx - xb) / (u2 - u1);
+            const double dy01 = (yb - ya) / (u1 - u0), dy12 = (ny - yb) / (u2 - u1);
+            const double axx = (dx12 - dx01) / (u2 - u0), ayy = (dy12 - dy01) / (u2 - u0);
+            const double bxx = dx01 - axx * (u0 + u1), byy = dy01 - ayy * (u0 + u1);
+            const double cxx = xa - axx * u0 * u0 - bxx * u0, cyy = ya - ayy * u0 * u0 - byy * u0;
+            const int64_t r = (int64_t)(k - 2) * p.np + i;
+            p.pa[r] = make_double2(axx, ayy);
+            p.pb[r] = make_double2(bxx, byy);
+            p.pc[r] = make_double2(cxx, cyy);
+        }
+        xa = xb; ya = yb; xb = nx; yb = ny;
+        u_prev2 = u_prev; u_prev = u_cur;
+    }
+    double sx = x0, sy = y0;                                      // env:320-321
+    const double sa = rng.uniform(-D2D_PI / 4, D2D_PI / 4);       // env:322
+    EnvView ev{&p, i, 0};
+    int n_obs = 0;
+    if (c.stage == 2) {                                           // env:329-333
+        sx = rng.uniform(100.0, c.W - 100.0);
+        sy = rng.uniform(100.0, c.H - 100.0);
+    } else if (c.stage == 3) {                                    // env:334-347
+        if (rng.u01() < c.spawn_chance) n_obs = sample_obstacles(p, ev, rng, 0, 1, 0.0, 100.0, false);
+    } else if (c.stage == 4) {                                    // env:348-361
+        if (rng.u01() < c.spawn_chance) n_obs = sample_obstacles(p, ev, rng, 0, 1, 0.0, 0.0, true);
+    } else if (c.stage == 5) {                                    // env:362-372
+        double nn = rng.normal(1.0, 4.0);
+        if (nn < 0.0 && nn > -3.0) nn = 1.0;
+        if (nn < -3.0) nn = 0.0;
+        if (nn != 0.0) {
+            int want = (int)ceil(nn);                             // `while num_obstacles < n` with float n
+            if (want < 0) want = 0;                               // nn == -3 exactly
+            if (want > D2D_MAX_OBS_ENV - 1) want = D2D_MAX_OBS_ENV - 1;
+            n_obs = sample_obstacles(p, ev, rng, 0, want, 0.0, 100.0, false);
+            n_obs = sample_obstacles(p, ev, rng, n_obs, 1, 0.0, 0.0, true);
+        }
+    }
+    spawn(s, c, sx, sy, sa);
+    s.episode = episode;
+    s.n_obs = n_obs;
+}
+
+}  // namespace d2d

@@ -1,0 +1,126 @@
+// drone2d_layout.h -- device-side data layout of the batched Drone2dEnv state.
+//
+// Everything is structure-of-arrays over the environment index so that the 32
+// lanes of a warp (one lane = one environment) touch 32 consecutive 16-byte
+// elements: every state access is one fully coalesced 512-byte LDG.128/STG.128
+// wavefront pair.  Pairs that are always used together are packed as double2.
+//
+//   pos  [3][N] double2  (px, py)      frame, left motor, right motor
+//   vel  [3][N] double2  (vx, vy)
+//   ang  [3][N] double2  (angle, omega)
+//   jacc [6][N] double2  (jx, jy)      cached pivot impulses left_1..3, right_1..3
+//   acc  [N]    double2  (path-error sum, reward sum)
+//   meta [N]    int4     (step counter, flags, episode number, n_obs)
+//   last [N]    double4-ish record of the last finished episode (2 x double2)
+//
+// Per-env tables (curriculum mode only; rows of waypoint/segment index major so
+// that lanes reading the same row coalesce):
+//   us   [MAX_WPS][N]        double
+//   wps  [MAX_WPS][N]        double2 (x, y)
+//   pa/pb/pc [MAX_WPS][N]    double2 (ax, ay) (bx, by) (cx, cy)   QPMI2D rows
+//   obxy [MAX_OBS_ENV][N]    double2 ; obr [MAX_OBS_ENV][N] double
+#pragma once
+#include <stddef.h>
+#include <stdint.h>
+
+#include "../../include/drone2d.h"
+
+#if defined(__CUDACC__)
+#define D2D_HD __host__ __device__
+#else
+#define D2D_HD
+#endif
+
+struct D2dLayout {
+    int64_t n;          // environments
+    int64_t np;         // padded to a multiple of 32 (row stride)
+    size_t off_pos, off_vel, off_ang, off_jacc, off_acc, off_meta, off_last;
+    size_t off_us, off_wps, off_pa, off_pb, off_pc, off_obxy, off_obr;
+    size_t bytes;
+    int per_env_tables;
+};
+
+static inline size_t d2d_align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+static inline void d2d_make_layout(D2dLayout *L, int64_t n, int per_env_tables)
+{
+    L->n = n;
+    L->np = (n + 31) / 32 * 32;
+    L->per_env_tables = per_env_tables;
+    size_t np = (size_t)L->np, o = 0;
+    auto take = [&](size_t bytes) { size_t r = o; o = d2d_align_up(o + bytes, 256); return r; };
+    L->off_pos = take(3 * np * 16);
+    L->off_vel = take(3 * np * 16);
+    L->off_ang = take(3 * np * 16);
+    L->off_jacc = take(6 * np * 16);
+    L->off_acc = take(np * 16);
+    L->off_meta = take(np * 16);
+    L->off_last = take(2 * np * 16);
+    L->off_us = L->off_wps = L->off_pa = L->off_pb = L->off_pc = L->off_obxy = L->off_obr = 0;
+    if (per_env_tables) {
+        L->off_us = take((size_t)D2D_MAX_WPS * np * 8);
+        L->off_wps = take((size_t)D2D_MAX_WPS * np * 16);
+        L->off_pa = take((size_t)D2D_MAX_WPS * np * 16);
+        L->off_pb = take((size_t)D2D_MAX_WPS * np * 16);
+        L->off_pc = take((size_t)D2D_MAX_WPS * np * 16);
+        L->off_obxy = take((size_t)D2D_MAX_OBS_ENV * np * 16);
+        L->off_obr = take((size_t)D2D_MAX_OBS_ENV * np * 8);
+    }
+    L->bytes = o;
+}
+
+// meta.y flag bits
+#define D2D_F_COLLIDED 1
+#define D2D_F_LATCHED 2
+#define D2D_F_DONE 4      // terminal state kept (auto_reset == 0)
+#define D2D_F_INIT 8      // spawned at least once (episode counter valid)
+
+// One shared scenario (test mode): path + circles, read-only, staged into shared memory.
+struct D2dSharedTables {
+    int n_wps, n_obs;
+    double us[D2D_MAX_WPS];
+    double wx[D2D_MAX_WPS], wy[D2D_MAX_WPS];
+    double ax[D2D_MAX_WPS], ay[D2D_MAX_WPS], bx[D2D_MAX_WPS], by[D2D_MAX_WPS], cx[D2D_MAX_WPS], cy[D2D_MAX_WPS];
+    double ox[D2D_MAX_OBS_SHARED], oy[D2D_MAX_OBS_SHARED], orad[D2D_MAX_OBS_SHARED];
+};
+
+// Constants derived once on the host from d2d_config (Drone.py:9-95 topology).
+struct D2dConst {
+    // config copy (arithmetic keys)
+    int mode, stage, n_steps, n_wps, corner_lo, corner_hi, random_path_spawn, use_Lambda, iterations;
+    double W, H, seg_len, lookahead;
+    double danger_range, danger_angle, k_ca;
+    double PA_band_edge, PA_scale, PP_vel_scale, PP_rew_max, PP_rew_min;
+    double rew_collision, reach_end_radius, rew_reach_end, AA_angle, AA_band, rew_AA;
+    double spawn_chance, sp_xmin, sp_xmax, sp_ymin, sp_ymax;
+    double gx, gy, dt, force_scale;
+    // derived
+    double R, d;                 // motor arm, joint spacing
+    double hw, hh;               // frame box half extents (50, 5)
+    double minv_f, iinv_f, minv_m, iinv_m;
+    double msum;                 // minv_m + minv_f
+    double bias_coef;            // -(1 - pow(0, dt)) / dt
+    double diag;                 // sqrt(W^2 + H^2)
+    uint32_t seed_lo, seed_hi;
+    int64_t env_id_base;
+};
+
+// Kernel parameter block.
+struct D2dParams {
+    int64_t n, np;
+    double2 *pos, *vel, *ang, *jacc, *acc, *last;
+    int4 *meta;
+    double *us;
+    double2 *wps, *pa, *pb, *pc, *obxy;
+    double *obr;
+    const D2dSharedTables *shared;
+    // I/O of one step
+    const float *actions;
+    float *obs, *reward, *terminal_obs;
+    uint8_t *done;
+    const uint8_t *mask;
+    double *obs64, *info, *stats;
+    uint64_t step_index;       // global step counter (keys the random-action stream)
+    int auto_reset;
+    D2dConst c;
+};

@@ -1,0 +1,357 @@
+"""Drone2dVecEnv -- the batched, device-resident replacement of the reference's
+`Drone2dEnv` (drone_2d_env.py:22-162, 394-615, 908-912) behind the SB3 VecEnv
+contract the reference consumes it through (`SubprocVecEnv`, main.py:88-101,190).
+
+PyTorch is plumbing only: it owns the device memory (one persistent state
+tensor + the I/O tensors) and the stream; every transition is ONE launch of the
+hand-written sm_100a kernel in csrc/drone2d.cu through the C ABI of
+include/drone2d.h.  There is no CPU fallback.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from .rl_config import STAGES, TEST_SCENARIOS, env_train_config, stage_from_timesteps
+from .scenarios import scenario_tables, spawn_rectangle
+from .spaces import Box
+
+INFO_KEYS = ("reward", "collision_avoidance_reward", "path_adherence", "path_progression", "collision_reward",
+             "reach_end_reward", "agressive_alpha_reward", "env_steps", "dist_closest_obs")
+STATS_KEYS = ("episodes", "n_successful_runs", "n_failed_runs", "n_collisions", "env_steps", "APE", "total_reward",
+              "reward", "collision_reward", "collision_avoidance_reward", "path_adherence", "path_progression",
+              "reach_end_reward", "agressive_alpha_reward", "steps_taken", "unused")
+_EMPTY_INFO = {}
+
+
+class _DeviceArray:
+    """Zero-copy view of library-owned device memory for torch.as_tensor."""
+
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
+
+
+def config_from_kwargs(kwargs):
+    """Map the reference's kwargs (rl_config.py:10-44, consumed at env:34-66) onto
+    struct d2d_config.  Unknown keys raise TypeError; the reference would raise
+    KeyError for missing ones -- here missing keys take the rl_config defaults."""
+    kw = dict(env_train_config)
+    extra = {"sim_num": 0}
+    for k, v in kwargs.items():
+        if k in kw:
+            kw[k] = v
+        elif k in extra:
+            extra[k] = v
+        else:
+            raise TypeError("unexpected keyword argument %r" % (k,))
+    mode, scenario = kw["mode"], kw["scenario"]
+    c = _lib.default_config()
+    if mode == "curriculum":
+        c.mode = _lib.MODE_CURRICULUM
+        if scenario in STAGES:
+            c.stage = int(scenario[-1])
+            c.stage_spawn_chance = {3: 0.6, 4: 1.0}.get(c.stage, 0.0)          # env:340-341,354-355
+        elif scenario in ("None", None):
+            c.stage, c.stage_spawn_chance = stage_from_timesteps(int(extra["sim_num"]))   # env:79-85,326-372
+        else:
+            raise ValueError("mode='curriculum' needs scenario in %s or 'None', got %r" % (STAGES, scenario))
+    elif mode == "test":
+        if scenario not in TEST_SCENARIOS:
+            # the reference crashes at env:316 (no waypoints) for stage_* in test mode
+            raise ValueError("mode='test' needs scenario in %s, got %r" % (TEST_SCENARIOS, scenario))
+        c.mode = _lib.MODE_TEST
+        c.spawn_xmin, c.spawn_xmax, c.spawn_ymin, c.spawn_ymax = spawn_rectangle(
+            scenario, kw["screensize_x"], kw["screensize_y"])
+    else:
+        raise ValueError("mode must be 'curriculum' or 'test', got %r" % (mode,))
+    c.n_steps = int(kw["n_steps"])
+    c.n_wps = int(kw["n_wps"])
+    c.spawn_corner_lo, c.spawn_corner_hi = int(kw["spawn_corners"][0]), int(kw["spawn_corners"][1])
+    c.random_path_spawn = 1 if kw["random_path_spawn"] is True else 0
+    c.use_Lambda = 1 if kw["use_Lambda"] is True else 0                       # `is True`, env:496
+    c.screen_x, c.screen_y = float(kw["screensize_x"]), float(kw["screensize_y"])
+    c.path_segment_length = float(kw["path_segment_length"])
+    for k in ("lookahead", "danger_range", "danger_angle", "abs_inv_CA_min_rew", "PA_band_edge", "PA_scale",
+              "PP_vel_scale", "PP_rew_max", "PP_rew_min", "rew_collision", "reach_end_radius", "rew_reach_end",
+              "AA_angle", "AA_band", "rew_AA"):
+        setattr(c, k, float(kw[k]))
+    return c, kw
+
+
+class Drone2dVecEnv:
+    """N independent Drone2dEnv instances stepped by one kernel launch.
+
+    SB3 VecEnv surface: num_envs, observation_space, action_space, reset(),
+    step_async()/step_wait()/step(), close(), seed(), get_attr/set_attr/
+    env_method/env_is_wrapped.  `step` auto-resets finished envs and puts the
+    last observation of the finished episode in infos[i]["terminal_observation"].
+
+    Device-resident surface (no host copies): reset_device(), step_device().
+
+    info_mode: "episode" (default) -> infos carry the reference's keys only for
+    envs that finished this step; "full" -> every env, every key of env:575-587
+    (slow for large N); "none" -> no per-env float64 taps at all (benchmarks).
+    """
+
+    metadata = {"render_modes": []}
+
+    def __init__(self, num_envs, device=None, seed=0, env_id_base=0, info_mode="episode", **kwargs):
+        if not torch.cuda.is_available():
+            raise RuntimeError("Drone2dVecEnv needs a CUDA device: there is no CPU fallback")
+        if info_mode not in ("episode", "full", "none"):
+            raise ValueError("info_mode must be 'episode', 'full' or 'none'")
+        self._L = _lib.load()
+        self.num_envs = int(num_envs)
+        self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+        self.cfg, self.kwargs = config_from_kwargs(kwargs)
+        self.info_mode = info_mode
+        self.seed_value = int(seed)
+        self.env_id_base = int(env_id_base)
+        n = self.num_envs
+        self.observation_space = Box(low=np.full(27, -1, dtype=np.float32), high=np.full(27, 1, dtype=np.float32),
+                                     dtype=np.float32)             # env:160-162 (values are NOT clipped)
+        self.action_space = Box(low=np.array([-1, -1], dtype=np.float32), high=np.array([1, 1], dtype=np.float32),
+                                dtype=np.float32)                  # env:155-157
+        nbytes = C.c_size_t()
+        _lib.check(self._L.d2d_state_bytes(C.byref(self.cfg), n, C.byref(nbytes)))
+        dev = self.device
+        self.state = torch.zeros(nbytes.value, dtype=torch.uint8, device=dev)     # the persistent SoA state
+        self.obs = torch.zeros((n, 27), dtype=torch.float32, device=dev)
+        self.rewards = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.dones = torch.zeros(n, dtype=torch.uint8, device=dev)
+        self.terminal_obs = torch.zeros((n, 27), dtype=torch.float32, device=dev)
+        self.actions = torch.zeros((n, 2), dtype=torch.float32, device=dev)
+        self._h = C.c_void_p()
+        _lib.check(self._L.d2d_create(C.byref(self.cfg), n, self.env_id_base, self.seed_value & (2 ** 64 - 1),
+                                      dev.index if dev.index is not None else torch.cuda.current_device(),
+                                      self.state.data_ptr(), nbytes.value, C.byref(self._h)))
+        self.obs64 = self.info = None
+        if info_mode != "none":
+            self.enable_taps()
+        if self.cfg.mode == _lib.MODE_TEST:
+            self.set_scenario(*scenario_tables(self.kwargs["scenario"], self.cfg.screen_x, self.cfg.screen_y))
+        # pinned host mirrors for the host-facing step()
+        self._h_act = torch.zeros((n, 2), dtype=torch.float32).pin_memory()
+        self._h_obs = torch.zeros((n, 27), dtype=torch.float32).pin_memory()
+        self._h_rew = torch.zeros(n, dtype=torch.float32).pin_memory()
+        self._h_done = torch.zeros(n, dtype=torch.uint8).pin_memory()
+        self._pending = None
+        self._closed = False
+
+    # ------------------------------------------------------------------ helpers
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    @staticmethod
+    def _dp(a):
+        return a.ctypes.data_as(C.POINTER(C.c_double))
+
+    def enable_taps(self):
+        """Allocate and register the float64 observation / info taps (include/drone2d.h: d2d_set_taps)."""
+        n = self.num_envs
+        self.obs64 = torch.zeros((n, 27), dtype=torch.float64, device=self.device)
+        self.info = torch.zeros((n, _lib.INFO_DOUBLES), dtype=torch.float64, device=self.device)
+        _lib.check(self._L.d2d_set_taps(self._h, self.obs64.data_ptr(), self.info.data_ptr()))
+
+    def disable_taps(self):
+        self.obs64 = self.info = None
+        _lib.check(self._L.d2d_set_taps(self._h, None, None))
+
+    def set_scenario(self, wps, us, xparams, yparams, obstacles):
+        """Upload one shared path + obstacle set (test mode)."""
+        wps, us = np.ascontiguousarray(wps, np.float64), np.ascontiguousarray(us, np.float64)
+        xp, yp = np.ascontiguousarray(xparams, np.float64), np.ascontiguousarray(yparams, np.float64)
+        ob = np.ascontiguousarray(obstacles, np.float64).reshape(-1, 3)
+        _lib.check(self._L.d2d_set_scenario(self._h, len(wps), self._dp(wps), self._dp(us), self._dp(xp), self._dp(yp),
+                                            len(ob), self._dp(ob) if len(ob) else None, self._stream()))
+        self.scenario = {"wps": wps, "us": us, "xparams": xp, "yparams": yp, "obstacles": ob}
+
+    # ------------------------------------------------------- device-resident API
+    def reset_device(self, mask=None):
+        """Re-spawn all envs (or those with mask != 0) on the device; returns the obs tensor [N, 27] (cuda)."""
+        m = None
+        if mask is not None:
+            m = mask.to(device=self.device, dtype=torch.uint8).contiguous()
+        _lib.check(self._L.d2d_reset(self._h, m.data_ptr() if m is not None else None, self.obs.data_ptr(),
+                                     self._stream()))
+        return self.obs
+
+    def step_device(self, actions=None, auto_reset=True, terminal_obs=True):
+        """One transition for all envs, nothing leaves the device.  `actions`: cuda
+        float32 [N, 2] (None -> in-kernel uniform random actions).  Returns the
+        persistent (obs, rewards, dones) tensors, overwritten by the next call."""
+        a = None
+        if actions is not None:
+            a = actions
+            if a.dtype != torch.float32 or not a.is_contiguous() or a.device != self.device:
+                a = a.to(device=self.device, dtype=torch.float32).contiguous()
+            if a.shape != (self.num_envs, 2):
+                raise ValueError("actions must have shape (%d, 2)" % self.num_envs)
+        _lib.check(self._L.d2d_step(self._h, a.data_ptr() if a is not None else None, self.obs.data_ptr(),
+                                    self.rewards.data_ptr(), self.dones.data_ptr(),
+                                    self.terminal_obs.data_ptr() if terminal_obs else None,
+                                    1 if auto_reset else 0, self._stream()))
+        return self.obs, self.rewards, self.dones
+
+    # ------------------------------------------------------------- SB3 VecEnv API
+    def reset(self):
+        self.reset_device()
+        return self.obs.cpu().numpy()
+
+    def step_async(self, actions):
+        self._pending = np.asarray(actions, dtype=np.float32).reshape(self.num_envs, 2)
+
+    def step_wait(self):
+        if self._pending is None:
+            raise RuntimeError("step_wait() without step_async()")
+        actions, self._pending = self._pending, None
+        self._h_act.copy_(torch.from_numpy(actions))
+        self.actions.copy_(self._h_act, non_blocking=True)
+        self.step_device(self.actions)
+        self._h_obs.copy_(self.obs, non_blocking=True)
+        self._h_rew.copy_(self.rewards, non_blocking=True)
+        self._h_done.copy_(self.dones, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        dones = self._h_done.numpy().astype(bool)
+        return self._h_obs.numpy().copy(), self._h_rew.numpy().copy(), dones, self._build_infos(dones)
+
+    def step(self, actions):
+        self.step_async(actions)
+        return self.step_wait()
+
+    def _info_row(self, row, done):
+        d = {k: float(row[j]) for j, k in enumerate(INFO_KEYS)}
+        d["env_steps"] = int(row[7])
+        if done:
+            bits = int(row[11])
+            d["n_collisions"] = int(bool(bits & 1) and not (bits & (2 | 4 | 8)))   # env:595-610 overwrite order
+            d["n_successful_runs"] = int(bool(bits & 2))
+            d["n_failed_runs"] = int(bool(bits & (1 | 4 | 8)))
+            d["APE"] = float(row[9])
+            d["total_reward"] = float(row[10])
+            d["flight_path"] = []            # env:612; positions are not recorded on the device
+            d["episode"] = {"r": float(row[10]), "l": int(row[7])}
+        return d
+
+    def _build_infos(self, dones):
+        n = self.num_envs
+        if self.info_mode == "full":
+            rows = self.info.cpu().numpy()
+            infos = [self._info_row(rows[i], dones[i]) for i in range(n)]
+            idx = np.flatnonzero(dones)
+        else:
+            infos = [_EMPTY_INFO] * n
+            idx = np.flatnonzero(dones)
+            if len(idx) and self.info is not None:
+                rows = self.info[torch.from_numpy(idx).to(self.device)].cpu().numpy()
+                for k, i in enumerate(idx):
+                    infos[i] = self._info_row(rows[k], True)
+            elif len(idx):
+                for i in idx:
+                    infos[i] = {}
+        if len(idx):
+            term = self.terminal_obs[torch.from_numpy(idx).to(self.device)].cpu().numpy()
+            for k, i in enumerate(idx):
+                infos[i]["terminal_observation"] = term[k]
+        return infos
+
+    def close(self):
+        if not self._closed and self._h:
+            self._L.d2d_destroy(self._h)
+            self._h = C.c_void_p()
+            self._closed = True
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+    def seed(self, seed=None):
+        """The reset stream is keyed at construction; returns the seeds SB3 expects."""
+        return [self.seed_value + self.env_id_base + i for i in range(self.num_envs)]
+
+    def get_attr(self, attr_name, indices=None):
+        idx = range(self.num_envs) if indices is None else ([indices] if isinstance(indices, int) else indices)
+        return [getattr(self, attr_name) for _ in idx]
+
+    def set_attr(self, attr_name, value, indices=None):
+        setattr(self, attr_name, value)
+
+    def env_method(self, method_name, *args, indices=None, **kwargs):
+        idx = range(self.num_envs) if indices is None else ([indices] if isinstance(indices, int) else indices)
+        return [getattr(self, method_name)(*args, **kwargs) for _ in idx]
+
+    def env_is_wrapped(self, wrapper_class, indices=None):
+        idx = range(self.num_envs) if indices is None else ([indices] if isinstance(indices, int) else indices)
+        return [False for _ in idx]
+
+    def render(self, mode="human"):
+        return None
+
+    def get_images(self):
+        return []
+
+    # ------------------------------------------------- state / tables / statistics
+    def get_state(self):
+        """float64 [N, 36] blob, layout documented in include/drone2d.h (d2d_get_state)."""
+        out = np.empty((self.num_envs, _lib.STATE_DOUBLES), dtype=np.float64)
+        _lib.check(self._L.d2d_get_state(self._h, self._dp(out)))
+        return out
+
+    def set_state(self, blob):
+        blob = np.ascontiguousarray(blob, dtype=np.float64)
+        if blob.shape != (self.num_envs, _lib.STATE_DOUBLES):
+            raise ValueError("state blob must have shape (%d, %d)" % (self.num_envs, _lib.STATE_DOUBLES))
+        _lib.check(self._L.d2d_set_state(self._h, self._dp(blob)))
+
+    def get_tables(self):
+        """Per-env path/obstacle tables (curriculum mode) as generated by the in-kernel reset."""
+        n = self.num_envs
+        t = {"wps": np.empty((n, _lib.MAX_WPS, 2)), "us": np.empty((n, _lib.MAX_WPS)),
+             "xparams": np.empty((n, _lib.MAX_WPS, 3)), "yparams": np.empty((n, _lib.MAX_WPS, 3)),
+             "n_obs": np.empty(n, dtype=np.int32), "obstacles": np.empty((n, _lib.MAX_OBS_ENV, 3))}
+        _lib.check(self._L.d2d_get_tables(self._h, self._dp(t["wps"]), self._dp(t["us"]), self._dp(t["xparams"]),
+                                          self._dp(t["yparams"]), t["n_obs"].ctypes.data_as(C.POINTER(C.c_int32)),
+                                          self._dp(t["obstacles"])))
+        return t
+
+    def set_tables(self, wps, us, xparams, yparams, n_obs, obstacles):
+        n = self.num_envs
+        arrs = [np.ascontiguousarray(a, np.float64) for a in (wps, us, xparams, yparams)]
+        n_obs = np.ascontiguousarray(n_obs, np.int32)
+        obstacles = np.ascontiguousarray(obstacles, np.float64)
+        want = [(n, _lib.MAX_WPS, 2), (n, _lib.MAX_WPS), (n, _lib.MAX_WPS, 3), (n, _lib.MAX_WPS, 3)]
+        for a, w in zip(arrs, want):
+            if a.shape != w:
+                raise ValueError("table shape %s != %s" % (a.shape, w))
+        if obstacles.shape != (n, _lib.MAX_OBS_ENV, 3) or n_obs.shape != (n,):
+            raise ValueError("obstacle table shapes")
+        _lib.check(self._L.d2d_set_tables(self._h, *[self._dp(a) for a in arrs],
+                                          n_obs.ctypes.data_as(C.POINTER(C.c_int32)), self._dp(obstacles)))
+
+    def closest_u(self, positions):
+        """QPMI2D.get_closest_u on arbitrary positions [N, 2] (env i uses its own path)."""
+        pos = torch.as_tensor(np.ascontiguousarray(positions, np.float64), device=self.device)
+        u = torch.empty(self.num_envs, dtype=torch.float64, device=self.device)
+        nfev = torch.empty(self.num_envs, dtype=torch.int32, device=self.device)
+        _lib.check(self._L.d2d_debug_closest_u(self._h, pos.data_ptr(), u.data_ptr(), nfev.data_ptr(), self._stream()))
+        return u.cpu().numpy(), nfev.cpu().numpy()
+
+    def episode_stats_tensor(self):
+        """Zero-copy float64[16] device tensor of the episode-statistics accumulator
+        (the vector that is all-reduced over ranks once per rollout)."""
+        ptr = C.c_void_p()
+        _lib.check(self._L.d2d_episode_stats_dev(self._h, C.byref(ptr)))
+        return torch.as_tensor(_DeviceArray(ptr.value, (_lib.STATS_DOUBLES,), "<f8"), device=self.device)
+
+    def episode_stats(self, reset=True):
+        out = np.zeros(_lib.STATS_DOUBLES, dtype=np.float64)
+        _lib.check(self._L.d2d_episode_stats(self._h, self._dp(out), 1 if reset else 0))
+        return dict(zip(STATS_KEYS, out.tolist()))
+
+    @property
+    def launch_count(self):
+        return int(self._L.d2d_launch_count(self._h))

@@ -1,0 +1,173 @@
+/* include/drone2d.h -- C ABI of the B200-native batched Drone2dEnv step.
+ *
+ * The reference has no native interface: the path sits behind the Python
+ * gym.Env methods of Drone2dEnv (reference drone_2d_custom_gym_env/
+ * drone_2d_env.py, "env" below).  Each entry point names the reference
+ * interface it replaces.  All functions return 0 on success or a negative
+ * D2D_E* code; d2d_last_error() gives the message.  No exceptions cross the
+ * ABI.  All "dev" pointers are device pointers owned by the caller (PyTorch
+ * tensors); the library allocates nothing per step.  Launches are asynchronous
+ * on the caller-supplied cudaStream_t (passed as void*); no host sync inside
+ * unless stated.  A handle is bound to one device and is not thread-safe.
+ */
+#ifndef DRONE2D_H
+#define DRONE2D_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define D2D_ABI_VERSION 1
+#define D2D_OBS_DIM 27          /* env:160-162,765-773 */
+#define D2D_ACT_DIM 2           /* env:155-157 */
+#define D2D_MAX_WPS 16          /* waypoints per path (reference uses 6..14) */
+#define D2D_MAX_OBS_SHARED 64   /* circles of a shared test scenario (max 58, test_scenarios.py:218-233) */
+#define D2D_MAX_OBS_ENV 32      /* per-env circles in curriculum stages (env:364-372 is unbounded:
+                                   ceil(N(1,4))+1; P(count > 32) ~ 3e-14, clamped) */
+#define D2D_STATE_DOUBLES 36    /* doubles per env in the d2d_get_state/d2d_set_state blob */
+#define D2D_INFO_DOUBLES 16     /* doubles per env in the per-step info blob */
+#define D2D_STATS_DOUBLES 16    /* doubles in the episode-statistics vector */
+
+#define D2D_OK 0
+#define D2D_EINVAL (-1)   /* bad argument */
+#define D2D_ECUDA (-2)    /* CUDA runtime error */
+#define D2D_ESTATE (-3)   /* call order / missing tables */
+
+enum { D2D_MODE_TEST = 0, D2D_MODE_CURRICULUM = 1 };
+
+/* rl_config.py:10-44: every key that reaches the arithmetic of the path, plus
+ * the Drone.py / init_pymunk constants (env:185,233,406).  Render keys and the
+ * dead keys (n_fall_steps, initial_throw, change_target; env:917-946 is never
+ * called) are accepted by the Python layer and do not reach the ABI. */
+typedef struct d2d_config {
+    int32_t abi_version;            /* D2D_ABI_VERSION */
+    int32_t mode;                   /* D2D_MODE_*  ('mode' kwarg) */
+    int32_t stage;                  /* 1..5 ('scenario' = stage_k) in curriculum mode */
+    int32_t n_steps;                /* 'n_steps' */
+    int32_t n_wps;                  /* 'n_wps' (curriculum); test mode: set by d2d_set_scenario */
+    int32_t spawn_corner_lo, spawn_corner_hi; /* 'spawn_corners' */
+    int32_t random_path_spawn;      /* 'random_path_spawn' */
+    int32_t use_Lambda;             /* 'use_Lambda' */
+    int32_t iterations;             /* pymunk Space.iterations (default 10) */
+    double screen_x, screen_y;      /* 'screensize_x/y' */
+    double path_segment_length;     /* 'path_segment_length' */
+    double lookahead;
+    double danger_range, danger_angle, abs_inv_CA_min_rew;
+    double PA_band_edge, PA_scale;
+    double PP_vel_scale, PP_rew_max, PP_rew_min;
+    double rew_collision, reach_end_radius, rew_reach_end;
+    double AA_angle, AA_band, rew_AA;
+    double stage_spawn_chance;      /* stage_3: 0.6, stage_4: 1.0 (env:340-358); explicit instead of
+                                       the checkpoint-filename glob of env:79-85 */
+    double spawn_xmin, spawn_xmax, spawn_ymin, spawn_ymax; /* test mode spawn rectangle (env:221-311) */
+    double mass_f, mass_m, width, height;                    /* Drone(x,y,a,20,100,0.2,0.4,0.4) */
+    double gravity_x, gravity_y, dt, force_scale;            /* env:185,406,150 */
+} d2d_config;
+
+typedef struct d2d_env d2d_env;
+
+/* Fill *cfg with rl_config.py:10-44 defaults (mode = curriculum, stage_1). */
+int d2d_default_config(d2d_config *cfg);
+
+/* Bytes of device memory the persistent SoA state + per-env tables of n_envs
+ * environments need.  The caller allocates it (256-byte aligned) and keeps it
+ * alive for the lifetime of the handle. */
+int d2d_state_bytes(const d2d_config *cfg, int64_t n_envs, size_t *bytes);
+
+/* Replaces Drone2dEnv.__init__(**kwargs) (env:33-162) for n_envs environments.
+ * env_id_base: global index of env 0 (rank offset) -- the reset RNG is keyed by
+ * (seed, global env id, episode), so results do not depend on the sharding. */
+int d2d_create(const d2d_config *cfg, int64_t n_envs, int64_t env_id_base, uint64_t seed,
+               int device, void *state_dev, size_t state_bytes, d2d_env **out);
+int d2d_destroy(d2d_env *env);
+
+/* Replaces test_scenarios.create_test_scenario (test_scenarios.py:169-246) as the
+ * table source in test mode: one path + obstacle set shared by all envs.  HOST
+ * pointers: wps [n_wps][2], us [n_wps], xparams/yparams [n_wps-2][3] (QPMI2D
+ * tables, predef_path.py:20-50), obstacles [n_obs][3] = (x, y, r). */
+int d2d_set_scenario(d2d_env *env, int n_wps, const double *wps, const double *us,
+                     const double *xparams, const double *yparams,
+                     int n_obs, const double *obstacles, void *stream);
+
+/* Curriculum mode, parity/checkpoint use: overwrite the per-env tables from
+ * HOST arrays wps [n][D2D_MAX_WPS][2], us [n][D2D_MAX_WPS],
+ * xparams/yparams [n][D2D_MAX_WPS][3], n_obs [n], obstacles [n][D2D_MAX_OBS_ENV][3].
+ * d2d_get_tables reads them back (what the in-kernel reset generated).  Both sync. */
+int d2d_set_tables(d2d_env *env, const double *wps, const double *us, const double *xparams,
+                   const double *yparams, const int32_t *n_obs, const double *obstacles);
+int d2d_get_tables(d2d_env *env, double *wps, double *us, double *xparams,
+                   double *yparams, int32_t *n_obs, double *obstacles);
+
+/* Replaces Drone2dEnv.reset() (env:908-912) for all envs (mask_dev == NULL) or
+ * the envs with mask_dev[i] != 0: fused re-spawn (env:182-392) from the
+ * counter-based RNG + first observation.  obs_dev: float32 [n][27]. */
+int d2d_reset(d2d_env *env, const uint8_t *mask_dev, float *obs_dev, void *stream);
+
+/* Replaces Drone2dEnv.step(action) (env:394-615) + the auto-reset SB3's VecEnv
+ * performs on done.  ONE kernel launch.
+ *   actions_dev      float32 [n][2]  (NULL: uniform random actions in [-1,1) from the
+ *                                     in-kernel Philox stream keyed by the step counter)
+ *   obs_dev          float32 [n][27] observation AFTER auto-reset (SB3 convention)
+ *   reward_dev       float32 [n]
+ *   done_dev         uint8   [n]
+ *   terminal_obs_dev float32 [n][27] or NULL: rows of finished envs receive the
+ *                                     last observation of the finished episode
+ *                                     (SB3 infos[i]["terminal_observation"])
+ *   auto_reset       0: finished envs are left in their terminal state (gym.Env semantics) */
+int d2d_step(d2d_env *env, const float *actions_dev, float *obs_dev, float *reward_dev,
+             uint8_t *done_dev, float *terminal_obs_dev, int auto_reset, void *stream);
+
+/* Same transition through HOST buffers (the end-to-end boundary): copies the
+ * actions host->device, launches the step, copies obs/reward/done back and
+ * synchronises the stream.  Uses pinned staging buffers owned by the handle. */
+int d2d_step_host(d2d_env *env, const float *actions_host, float *obs_host, float *reward_host,
+                  uint8_t *done_host, int auto_reset, void *stream);
+
+/* Optional float64 taps of the LAST d2d_step/d2d_reset, for parity tests and the
+ * info dict (env:575-613).  Pass device pointers (or NULL to disable):
+ *   obs64_dev  double [n][27]               observation before the f32 cast (terminal obs for finished envs)
+ *   info_dev   double [n][D2D_INFO_DOUBLES]: reward, collision_avoidance_reward,
+ *              path_adherence, path_progression, collision_reward, reach_end_reward,
+ *              agressive_alpha_reward, env_steps, dist_closest_obs, APE, total_reward,
+ *              end-condition bits (1 collision | 2 reached | 4 time | 8 alpha),
+ *              u* (closest path parameter), Brent evaluations, nearest-obstacle
+ *              indices packed (i0 + 256*i1 + 65536*i2, 255 = none), episode number */
+int d2d_set_taps(d2d_env *env, double *obs64_dev, double *info_dev);
+
+/* State blob (HOST, float64 [n][D2D_STATE_DOUBLES], sync): per env
+ *   [0..17]  frame, left motor, right motor: px, py, vx, vy, angle, omega
+ *   [18..29] cached pivot impulses jx,jy of left_1..3, right_1..3
+ *   [30] collided  [31] look-ahead latched  [32] step counter
+ *   [33] path-error sum  [34] reward sum  [35] episode number */
+int d2d_get_state(d2d_env *env, double *state_host);
+int d2d_set_state(d2d_env *env, const double *state_host);
+
+/* Episode statistics accumulated on the device since the last call with
+ * reset_after != 0 (HOST, double [D2D_STATS_DOUBLES], sync):
+ *   episodes, successes, failures, collisions, sum env_steps, sum APE,
+ *   sum total_reward, then the sums of the LAST-step info terms that
+ *   tensorboardlogger.py:80-88 averages: reward, collision_reward,
+ *   collision_avoidance_reward, path_adherence, path_progression,
+ *   reach_end_reward, agressive_alpha_reward; [14] = steps taken, [15] unused. */
+int d2d_episode_stats(d2d_env *env, double *stats_host, int reset_after);
+/* Device pointer of the same vector (for an NCCL all-reduce over ranks). */
+int d2d_episode_stats_dev(d2d_env *env, double **stats_dev);
+
+/* Debug tap of the closest-point search (QPMI2D.get_closest_u, predef_path.py:226-248)
+ * on arbitrary positions: pos_dev double [n][2] -> u_dev double [n], nfev_dev int32 [n].
+ * Env i uses its own path tables. */
+int d2d_debug_closest_u(d2d_env *env, const double *pos_dev, double *u_dev, int32_t *nfev_dev, void *stream);
+
+/* Number of kernels this library has launched on this handle. */
+int64_t d2d_launch_count(const d2d_env *env);
+
+const char *d2d_last_error(void);
+int d2d_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DRONE2D_H */
