@@ -55,7 +55,7 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.build()
+    path = os.environ.get("D2D_LIB") or _build.build()     # D2D_LIB: load a specific build (kernel tuning)
     if not os.path.exists(path):
         raise D2DError("CUDA extension %s is missing" % path)
     L = C.CDLL(path)

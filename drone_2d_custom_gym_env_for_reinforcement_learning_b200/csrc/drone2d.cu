@@ -16,7 +16,7 @@
 #define D2D_BLOCK 128
 #endif
 #ifndef D2D_MIN_BLOCKS
-#define D2D_MIN_BLOCKS 3
+#define D2D_MIN_BLOCKS 4
 #endif
 
 using namespace d2d;
@@ -30,15 +30,15 @@ struct ViewOf;
 template <>
 struct ViewOf<true> {
     typedef EnvView type;
-    static __device__ __forceinline__ EnvView make(const D2dParams &p, const D2dSharedTables *, int64_t i, int n_obs)
+    static __device__ __forceinline__ EnvView make(const D2dParams &p, const D2dSharedTables *, int64_t i, int n_obs, int par)
     {
-        return EnvView{&p, i, n_obs};
+        return EnvView{&p, i, n_obs, par};
     }
 };
 template <>
 struct ViewOf<false> {
     typedef SharedView type;
-    static __device__ __forceinline__ SharedView make(const D2dParams &, const D2dSharedTables *t, int64_t, int)
+    static __device__ __forceinline__ SharedView make(const D2dParams &, const D2dSharedTables *t, int64_t, int, int)
     {
         return SharedView{t};
     }
@@ -51,9 +51,75 @@ __device__ __forceinline__ void stage_shared_tables(const D2dParams &p, D2dShare
     for (int k = tid; k < (int)(sizeof(D2dSharedTables) / sizeof(int)); k += nthreads) d[k] = src[k];
 }
 
+// First observation of a freshly spawned drone (at rest at (x, y, angle)) in episode tables
+// `par`: Drone2dEnv.reset() -> get_observation() (env:908-912).  Returns the flag bits the
+// observation sets (the look-ahead latch can already engage, env:739-741).  One out-of-line
+// copy shared by the refill warps, the reset kernel and the in-lane fallback.
+template <bool PER_ENV>
+__device__ __noinline__ int first_observation(const D2dParams &p, const D2dSharedTables *tab, int64_t i, double x,
+                                              double y, double angle, int n_obs, int par, float *row, double *o64,
+                                              double *info, int episode)
+{
+    EnvState s;
+    s.px[0] = x; s.py[0] = y; s.an[0] = angle; s.vx[0] = 0.0; s.vy[0] = 0.0; s.om[0] = 0.0;
+    s.flags = 0;
+    double rc0, rs0;
+    sincos(angle, &rs0, &rc0);
+    typename ViewOf<PER_ENV>::type v = ViewOf<PER_ENV>::make(p, tab, i, n_obs, par);
+    Nearest nr;
+    scan_obstacles(v, p.c, x, y, rc0, rs0, false, nr);
+    auto put = [&](int j, double val) {
+        if (row) row[j] = (float)val;
+        if (o64) o64[j] = val;
+    };
+    ObsAux ax;
+    observe(v, p.c, s, rc0, rs0, nr, put, ax);
+    if (info) {
+        for (int k = 0; k < D2D_INFO_DOUBLES; k++) info[k] = 0.0;
+        info[12] = ax.u_star; info[13] = (double)ax.nfev; info[14] = (double)ax.near_packed; info[15] = (double)episode;
+    }
+    return s.flags & D2D_F_LATCHED;
+}
+
+// Prefetch of episode `meta.z + 1` of env e into its staging slot (tables buffer = the one
+// that is not live), in two stages so that neither is longer than a main lane's step:
+//   stage A  sample the episode: tables + spawn pose            (stg_meta = {-1, n_obs, 0, target})
+//   stage B  first observation of the staged episode, publish   (stg_meta = {target, n_obs, latch, target})
+template <bool PER_ENV>
+__device__ __forceinline__ void stage_sample(const D2dParams &p, int64_t e)
+{
+    const int4 m = p.meta[e];
+    const int target = m.z + 1;
+    const int par = (m.y & D2D_F_PARITY) ? 0 : 1;
+    const ResetOut ro = reset_env<PER_ENV>(p, e, target, par);
+    p.stg_xy[e] = make_double2(ro.x, ro.y);
+    p.stg_an[e] = make_double2(ro.angle, 0.0);
+    p.stg_meta[e] = make_int4(-1, ro.n_obs, par, target);
+}
+
+template <bool PER_ENV>
+__device__ __forceinline__ void stage_observe(const D2dParams &p, const D2dSharedTables *tab, int64_t e, int target)
+{
+    const int4 sm = p.stg_meta[e];
+    const int par = sm.z;
+    // the env moved on (in-lane fallback) or the slot was re-sampled for a later episode: drop the stale task
+    if (sm.w != target || sm.x != -1 || p.meta[e].z + 1 != target) return;
+    const double2 xy = p.stg_xy[e];
+    const int latch = first_observation<PER_ENV>(p, tab, e, xy.x, xy.y, p.stg_an[e].x, sm.y, par,
+                                                 p.stg_obs + e * D2D_OBS_DIM, nullptr, nullptr, target);
+    __threadfence();
+    p.stg_meta[e] = make_int4(target, sm.y, latch, target);
+}
+
 // The fused step: thrust -> cpSpaceStep -> sensor overlap -> nearest-3 ->
 // closest/look-ahead point -> 27-float observation -> reward -> termination ->
-// episode statistics -> auto-reset (+ first observation of the new episode).
+// episode statistics -> auto-reset.  Grid = [sample blocks | observe blocks | main blocks]:
+//   main blocks    one lane per environment; a finished env swaps in its prefetched episode
+//                  (spawn pose + first observation + table-buffer flip) and queues a refill;
+//   sample blocks  draw the next episode of the envs that consumed their slot one step ago;
+//   observe blocks compute the first observation of the episodes drawn one step ago.
+// The sampling and the first closest-point search thus run concurrently with the main
+// lanes, two steps ahead of any possible use, instead of extending a finished lane.
 template <bool PER_ENV>
 __global__ void __launch_bounds__(D2D_BLOCK, D2D_MIN_BLOCKS) d2d_step_kernel(const __grid_constant__ D2dParams p)
 {
@@ -63,14 +129,42 @@ __global__ void __launch_bounds__(D2D_BLOCK, D2D_MIN_BLOCKS) d2d_step_kernel(con
     __shared__ D2dSharedTables s_tab;
 
     const int tid = threadIdx.x;
-    const int64_t i = (int64_t)blockIdx.x * D2D_BLOCK + tid;
-    const bool valid = i < p.n;
     const D2dConst &c = p.c;
+    const int q_write = (int)(p.step_index % 3), q_read = (int)((p.step_index + 2) % 3), q_clear = (int)((p.step_index + 1) % 3);
 
     if (!PER_ENV) stage_shared_tables(p, &s_tab, tid, D2D_BLOCK);
     if (tid < D2D_STATS_DOUBLES) s_stats[tid] = 0.0;
     if (tid == 0) s_any_done = 0;
+    if (blockIdx.x == 0 && tid == 0) { p.qcount[q_clear] = 0; p.qcount[3 + q_clear] = 0; }
     __syncthreads();
+
+    int *qa = p.queue, *qb = p.queue + 3 * p.np, *qb_tgt = p.queue + 6 * p.np;
+    int *qa_cnt = p.qcount, *qb_cnt = p.qcount + 3;
+    if ((int)blockIdx.x < 2 * p.refill_blocks) {
+        const int total = p.refill_blocks * D2D_BLOCK;
+        if ((int)blockIdx.x < p.refill_blocks) {
+            // ---- sample role: queue A of the previous step -> queue B of this step ----
+            const int cnt = qa_cnt[q_read];
+            for (int t = blockIdx.x * D2D_BLOCK + tid; t < cnt; t += total) {
+                const int e = qa[(int64_t)q_read * p.np + t];
+                stage_sample<PER_ENV>(p, e);
+                const int slot = atomicAdd(&qb_cnt[q_write], 1);
+                qb[(int64_t)q_write * p.np + slot] = e;
+                qb_tgt[(int64_t)q_write * p.np + slot] = p.stg_meta[e].w;
+            }
+        } else {
+            // ---- observe role: queue B of the previous step ----
+            const int cnt = qb_cnt[q_read];
+            for (int t = (blockIdx.x - p.refill_blocks) * D2D_BLOCK + tid; t < cnt; t += total)
+                stage_observe<PER_ENV>(p, &s_tab, (int64_t)qb[(int64_t)q_read * p.np + t],
+                                       qb_tgt[(int64_t)q_read * p.np + t]);
+        }
+        return;
+    }
+
+    const int64_t blk = (int64_t)blockIdx.x - 2 * p.refill_blocks;
+    const int64_t i = blk * D2D_BLOCK + tid;
+    const bool valid = i < p.n;
 
     if (valid) {
         EnvState s;
@@ -90,38 +184,35 @@ __global__ void __launch_bounds__(D2D_BLOCK, D2D_MIN_BLOCKS) d2d_step_kernel(con
         double rc0, rs0;
         physics_step(s, c, (double)act.x, (double)act.y, rc0, rs0);
         s.steps += 1;                                               // env:407
+        store_bodies(p, i, s);
 
-        bool second = false;
         float *row = &s_obs[tid * D2D_OBS_DIM];
-#pragma unroll 1
-        for (;;) {
-            typename ViewOf<PER_ENV>::type v = ViewOf<PER_ENV>::make(p, &s_tab, i, s.n_obs);
-            Nearest nr;
-            const bool hit = scan_obstacles(v, c, s.px[0], s.py[0], rc0, rs0, !second, nr);
-            if (hit) s.flags |= D2D_F_COLLIDED;                     // begin callback, env:17-19
+        const int par = (s.flags & D2D_F_PARITY) ? 1 : 0;
+        typename ViewOf<PER_ENV>::type v = ViewOf<PER_ENV>::make(p, &s_tab, i, s.n_obs, par);
+        Nearest nr;
+        const bool hit = scan_obstacles(v, c, s.px[0], s.py[0], rc0, rs0, true, nr);
+        if (hit) s.flags |= D2D_F_COLLIDED;                         // begin callback, env:17-19
 
-            double *o64 = (p.obs64 && !second) ? p.obs64 + i * D2D_OBS_DIM : nullptr;
-            auto put = [&](int j, double val) {
-                row[j] = (float)val;
-                if (o64) o64[j] = val;
-            };
-            ObsAux ax;
-            observe(v, c, s, rc0, rs0, nr, put, ax);
-            if (second) break;
+        double *o64 = p.obs64 ? p.obs64 + i * D2D_OBS_DIM : nullptr;
+        auto put = [&](int j, double val) {
+            row[j] = (float)val;
+            if (o64) o64[j] = val;
+        };
+        ObsAux ax;
+        observe(v, c, s, rc0, rs0, nr, put, ax);
 
-            StepResult r;
-            reward_and_done(c, s, ax, v.n_obs() > 0, r);
-            p.reward[i] = (float)r.reward;
-            p.done[i] = r.done ? 1 : 0;
-            if (p.info) {
-                double *f = p.info + i * D2D_INFO_DOUBLES;
-                f[0] = r.reward; f[1] = r.r_CA; f[2] = r.r_PA; f[3] = r.r_PP; f[4] = r.r_coll; f[5] = r.r_end;
-                f[6] = r.r_AA; f[7] = (double)s.steps; f[8] = r.d1; f[9] = r.ape; f[10] = s.total_reward;
-                f[11] = (double)r.end_bits; f[12] = ax.u_star; f[13] = (double)ax.nfev;
-                f[14] = (double)ax.near_packed; f[15] = (double)s.episode;
-            }
-            if (!r.done) break;
-
+        StepResult r;
+        reward_and_done(c, s, ax, v.n_obs() > 0, r);
+        p.reward[i] = (float)r.reward;
+        p.done[i] = r.done ? 1 : 0;
+        if (p.info) {
+            double *f = p.info + i * D2D_INFO_DOUBLES;
+            f[0] = r.reward; f[1] = r.r_CA; f[2] = r.r_PA; f[3] = r.r_PP; f[4] = r.r_coll; f[5] = r.r_end;
+            f[6] = r.r_AA; f[7] = (double)s.steps; f[8] = r.d1; f[9] = r.ape; f[10] = s.total_reward;
+            f[11] = (double)r.end_bits; f[12] = ax.u_star; f[13] = (double)ax.nfev;
+            f[14] = (double)ax.near_packed; f[15] = (double)s.episode;
+        }
+        if (r.done) {
             if (!(s.flags & D2D_F_DONE)) {
                 // episode statistics (env:593-613; main.py:272-282; tensorboardlogger.py:80-88)
                 const int b = r.end_bits;
@@ -145,24 +236,47 @@ __global__ void __launch_bounds__(D2D_BLOCK, D2D_MIN_BLOCKS) d2d_step_kernel(con
             }
             if (!p.auto_reset) {
                 s.flags |= D2D_F_DONE;
-                break;
-            }
-            if (p.terminal_obs) {
-                float *t = p.terminal_obs + i * D2D_OBS_DIM;
+            } else {
+                if (p.terminal_obs) {
+                    float *t = p.terminal_obs + i * D2D_OBS_DIM;
 #pragma unroll
-                for (int j = 0; j < D2D_OBS_DIM; j++) t[j] = row[j];
+                    for (int j = 0; j < D2D_OBS_DIM; j++) t[j] = row[j];
+                }
+                const int next_ep = s.episode + 1;
+                const int4 sm = p.stg_meta[i];
+                double nx, ny, na;
+                int n_obs, new_flags;
+                if (sm.x == next_ep) {
+                    // swap in the prefetched episode: flip the table buffer, take pose + first observation
+                    const double2 xy = p.stg_xy[i];
+                    nx = xy.x; ny = xy.y; na = p.stg_an[i].x;
+                    n_obs = sm.y;
+                    new_flags = D2D_F_INIT | (par ? 0 : D2D_F_PARITY) | (sm.z ? D2D_F_LATCHED : 0);
+                    const float *so = p.stg_obs + i * D2D_OBS_DIM;
+#pragma unroll
+                    for (int j = 0; j < D2D_OBS_DIM; j++) row[j] = so[j];
+                } else {
+                    // slot not ready (episode ended one step after the previous one, or state was
+                    // injected): sample in the lane, into the live table buffer
+                    const ResetOut ro = reset_env<PER_ENV>(p, i, next_ep, par);
+                    nx = ro.x; ny = ro.y; na = ro.angle; n_obs = ro.n_obs;
+                    new_flags = D2D_F_INIT | (par ? D2D_F_PARITY : 0);
+                    new_flags |= first_observation<PER_ENV>(p, &s_tab, i, nx, ny, na, n_obs, par, row, nullptr, nullptr, next_ep);
+                }
+                spawn(s, c, nx, ny, na);
+                s.flags = new_flags; s.episode = next_ep; s.n_obs = n_obs;
+                store_bodies(p, i, s);
+                // ask the next step's refill blocks for episode next_ep + 1
+                qa[(int64_t)q_write * p.np + atomicAdd(&qa_cnt[q_write], 1)] = (int)i;
             }
-            reset_env<PER_ENV>(p, i, s, s.episode + 1);
-            sincos(s.an[0], &rs0, &rc0);
-            second = true;
         }
-        store_state(p, i, s);
+        store_scalars(p, i, s);
     }
     __syncthreads();
 
     // coalesced store of the block's [BLOCK][27] float32 observation tile
     {
-        const int64_t base = (int64_t)blockIdx.x * D2D_BLOCK;
+        const int64_t base = blk * D2D_BLOCK;
         const int rows = (int)min((int64_t)D2D_BLOCK, p.n - base);
         if (rows == D2D_BLOCK) {
             const float4 *src = reinterpret_cast<const float4 *>(s_obs);
@@ -176,7 +290,8 @@ __global__ void __launch_bounds__(D2D_BLOCK, D2D_MIN_BLOCKS) d2d_step_kernel(con
     if (s_any_done && tid < 14) atomicAdd(&p.stats[tid], s_stats[tid]);
 }
 
-// Drone2dEnv.reset() for all / masked envs: re-spawn + first observation.
+// Drone2dEnv.reset() for all / masked envs: re-spawn + first observation, and prefetch of
+// the episode after it.
 template <bool PER_ENV>
 __global__ void __launch_bounds__(D2D_BLOCK) d2d_reset_kernel(const __grid_constant__ D2dParams p)
 {
@@ -188,29 +303,21 @@ __global__ void __launch_bounds__(D2D_BLOCK) d2d_reset_kernel(const __grid_const
     if (i >= p.n) return;
     if (p.mask && !p.mask[i]) return;
     const D2dConst &c = p.c;
+    const int4 m = p.meta[i];
+    const int episode = (m.y & D2D_F_INIT) ? m.z + 1 : 0;
+    const int par = (m.y & D2D_F_PARITY) ? 1 : 0;
+    const ResetOut ro = reset_env<PER_ENV>(p, i, episode, par);
+    const int latch = first_observation<PER_ENV>(p, &s_tab, i, ro.x, ro.y, ro.angle, ro.n_obs, par,
+                                                 p.obs ? p.obs + i * D2D_OBS_DIM : nullptr,
+                                                 p.obs64 ? p.obs64 + i * D2D_OBS_DIM : nullptr,
+                                                 p.info ? p.info + i * D2D_INFO_DOUBLES : nullptr, episode);
     EnvState s;
-    load_state(p, i, s);
-    const int episode = (s.flags & D2D_F_INIT) ? s.episode + 1 : 0;
-    reset_env<PER_ENV>(p, i, s, episode);
-    double rc0, rs0;
-    sincos(s.an[0], &rs0, &rc0);
-    typename ViewOf<PER_ENV>::type v = ViewOf<PER_ENV>::make(p, &s_tab, i, s.n_obs);
-    Nearest nr;
-    scan_obstacles(v, c, s.px[0], s.py[0], rc0, rs0, false, nr);
-    float *row = p.obs ? p.obs + i * D2D_OBS_DIM : nullptr;
-    double *o64 = p.obs64 ? p.obs64 + i * D2D_OBS_DIM : nullptr;
-    auto put = [&](int j, double val) {
-        if (row) row[j] = (float)val;
-        if (o64) o64[j] = val;
-    };
-    ObsAux ax;
-    observe(v, c, s, rc0, rs0, nr, put, ax);
-    if (p.info) {
-        double *f = p.info + i * D2D_INFO_DOUBLES;
-        for (int k = 0; k < D2D_INFO_DOUBLES; k++) f[k] = 0.0;
-        f[12] = ax.u_star; f[13] = (double)ax.nfev; f[14] = (double)ax.near_packed; f[15] = (double)s.episode;
-    }
+    spawn(s, c, ro.x, ro.y, ro.angle);
+    s.flags = D2D_F_INIT | (par ? D2D_F_PARITY : 0) | latch;
+    s.episode = episode; s.n_obs = ro.n_obs;
     store_state(p, i, s);
+    stage_sample<PER_ENV>(p, i);
+    stage_observe<PER_ENV>(p, &s_tab, i, episode + 1);
 }
 
 template <bool PER_ENV>
@@ -222,9 +329,10 @@ __global__ void d2d_closest_u_kernel(const __grid_constant__ D2dParams p, const 
     if (!PER_ENV) stage_shared_tables(p, &s_tab, tid, blockDim.x);
     __syncthreads();
     if (i >= p.n) return;
-    typename ViewOf<PER_ENV>::type v = ViewOf<PER_ENV>::make(p, &s_tab, i, 0);
+    typename ViewOf<PER_ENV>::type v = ViewOf<PER_ENV>::make(p, &s_tab, i, 0, (p.meta[i].y & D2D_F_PARITY) ? 1 : 0);
     int nfev;
-    u_out[i] = closest_u(v, pos[2 * i], pos[2 * i + 1], nfev);
+    PathCursor<typename ViewOf<PER_ENV>::type> pc(v);
+    u_out[i] = closest_u(pc, pos[2 * i], pos[2 * i + 1], nfev);
     nfev_out[i] = nfev;
 }
 
@@ -252,7 +360,7 @@ __global__ void d2d_pack_state_kernel(const D2dParams p, double *blob, int to_bl
             s.an[k] = b[6 * k + 4]; s.om[k] = b[6 * k + 5];
         }
         for (int j = 0; j < 6; j++) { s.jx[j] = b[18 + 2 * j]; s.jy[j] = b[19 + 2 * j]; }
-        s.flags = D2D_F_INIT | (b[30] != 0.0 ? D2D_F_COLLIDED : 0) | (b[31] != 0.0 ? D2D_F_LATCHED : 0);
+        s.flags = D2D_F_INIT | (s.flags & D2D_F_PARITY) | (b[30] != 0.0 ? D2D_F_COLLIDED : 0) | (b[31] != 0.0 ? D2D_F_LATCHED : 0);
         s.steps = (int)b[32]; s.path_error = b[33]; s.total_reward = b[34]; s.episode = (int)b[35];
         store_state(p, i, s);
     }
@@ -264,8 +372,9 @@ __global__ void d2d_pack_tables_kernel(const D2dParams p, double *wps, double *u
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= p.n) return;
+    const int par = (p.meta[i].y & D2D_F_PARITY) ? 1 : 0;          // the live episode's buffer
     for (int k = 0; k < D2D_MAX_WPS; k++) {
-        const int64_t r = (int64_t)k * p.np + i;
+        const int64_t r = (int64_t)(par * D2D_MAX_WPS + k) * p.np + i;
         double *w = wps + (i * D2D_MAX_WPS + k) * 2;
         double *x = xp + (i * D2D_MAX_WPS + k) * 3, *y = yp + (i * D2D_MAX_WPS + k) * 3;
         if (to_host) {
@@ -278,7 +387,7 @@ __global__ void d2d_pack_tables_kernel(const D2dParams p, double *wps, double *u
         }
     }
     for (int k = 0; k < D2D_MAX_OBS_ENV; k++) {
-        const int64_t r = (int64_t)k * p.np + i;
+        const int64_t r = (int64_t)(par * D2D_MAX_OBS_ENV + k) * p.np + i;
         double *o = obst + (i * D2D_MAX_OBS_ENV + k) * 3;
         if (to_host) {
             const double2 xy = p.obxy[r];
@@ -467,6 +576,11 @@ int d2d_create(const d2d_config *cfg, int64_t n_envs, int64_t env_id_base, uint6
     p.pos = (double2 *)(base + L.off_pos); p.vel = (double2 *)(base + L.off_vel); p.ang = (double2 *)(base + L.off_ang);
     p.jacc = (double2 *)(base + L.off_jacc); p.acc = (double2 *)(base + L.off_acc); p.meta = (int4 *)(base + L.off_meta);
     p.last = (double2 *)(base + L.off_last);
+    p.stg_xy = (double2 *)(base + L.off_stg_xy); p.stg_an = (double2 *)(base + L.off_stg_an);
+    p.stg_meta = (int4 *)(base + L.off_stg_meta); p.stg_obs = (float *)(base + L.off_stg_obs);
+    p.queue = (int *)(base + L.off_queue); p.qcount = (int *)(base + L.off_qcount);
+    // refill capacity: one lane per 32 envs (a larger backlog is handled by striding over the queue)
+    p.refill_blocks = (int)((L.n + 32 * D2D_BLOCK - 1) / (32 * D2D_BLOCK));
     if (L.per_env_tables) {
         p.us = (double *)(base + L.off_us); p.wps = (double2 *)(base + L.off_wps);
         p.pa = (double2 *)(base + L.off_pa); p.pb = (double2 *)(base + L.off_pb); p.pc = (double2 *)(base + L.off_pc);
@@ -628,7 +742,7 @@ int d2d_step(d2d_env *e, const float *actions_dev, float *obs_dev, float *reward
     p.actions = actions_dev; p.obs = obs_dev; p.reward = reward_dev; p.done = done_dev;
     p.terminal_obs = terminal_obs_dev; p.auto_reset = auto_reset; p.step_index = e->step_index++;
     cudaStream_t st = (cudaStream_t)stream;
-    const int grid = grid_for(p.n, D2D_BLOCK);
+    const int grid = grid_for(p.n, D2D_BLOCK) + 2 * p.refill_blocks;
     if (e->cfg.mode == D2D_MODE_CURRICULUM) d2d_step_kernel<true><<<grid, D2D_BLOCK, 0, st>>>(p);
     else d2d_step_kernel<false><<<grid, D2D_BLOCK, 0, st>>>(p);
     e->launches++;

@@ -153,17 +153,20 @@ struct EnvView {
     const D2dParams *p;
     int64_t i;
     int nobs;
+    int par;     // table buffer (0/1) this view reads
+    __device__ __forceinline__ int64_t wrow(int k) const { return ((int64_t)(par * D2D_MAX_WPS + k)) * p->np + i; }
+    __device__ __forceinline__ int64_t orow(int k) const { return ((int64_t)(par * D2D_MAX_OBS_ENV + k)) * p->np + i; }
     __device__ __forceinline__ int n_wps() const { return p->c.n_wps; }
     __device__ __forceinline__ int n_obs() const { return nobs; }
-    __device__ __forceinline__ double us(int k) const { return p->us[(int64_t)k * p->np + i]; }
-    __device__ __forceinline__ double2 wp(int k) const { return p->wps[(int64_t)k * p->np + i]; }
-    __device__ __forceinline__ double2 pa(int r) const { return p->pa[(int64_t)r * p->np + i]; }
-    __device__ __forceinline__ double2 pb(int r) const { return p->pb[(int64_t)r * p->np + i]; }
-    __device__ __forceinline__ double2 pc(int r) const { return p->pc[(int64_t)r * p->np + i]; }
+    __device__ __forceinline__ double us(int k) const { return p->us[wrow(k)]; }
+    __device__ __forceinline__ double2 wp(int k) const { return p->wps[wrow(k)]; }
+    __device__ __forceinline__ double2 pa(int r) const { return p->pa[wrow(r)]; }
+    __device__ __forceinline__ double2 pb(int r) const { return p->pb[wrow(r)]; }
+    __device__ __forceinline__ double2 pc(int r) const { return p->pc[wrow(r)]; }
     __device__ __forceinline__ void obstacle(int k, double &x, double &y, double &r) const
     {
-        double2 xy = p->obxy[(int64_t)k * p->np + i];
-        x = xy.x; y = xy.y; r = p->obr[(int64_t)k * p->np + i];
+        const double2 xy = p->obxy[orow(k)];
+        x = xy.x; y = xy.y; r = p->obr[orow(k)];
     }
 };
 
@@ -245,24 +248,98 @@ __device__ __forceinline__ void path_gradient(const V &v, double u, double &dx, 
     dy = S::add(S::mul(S::mul(a.y, u), 2.0), b.y);
 }
 
-// np.linalg.norm(path(u) - pos) (predef_path.py:246): sqrt(x.dot(x)) with BLAS
-// ddot's fused accumulate -> sqrt(fma(dy, dy, dx*dx)).
+// ---------------------------------------------------------------------------
+// PathCursor: path_eval with the segment data of the last evaluation kept in
+// registers.  Brent's iterates stay inside one blending segment after the first
+// few golden-section steps, so most evaluations need no table access and no
+// segment search.  The arithmetic performed for a given u is IDENTICAL to
+// path_eval (same strict operations, same order) -- only the loads are cached.
+//   kind 0: single polynomial, first stretch   valid for us0 <= u <= us1
+//   kind 1: single polynomial, last stretch    valid for u >= us[-2] - 0.001
+//   kind 2: blend of rows n-1, n (n >= 1)      valid for us[n] < u <= us[n+1] and u < last_start
+//   kind 3: u < us0: blend of the LAST row and row 0 (Python index -1), n = 0
+// (first/last are disjoint for n_wps >= 4 with increasing us, which d2d_set_scenario /
+//  d2d_set_tables / the reset guarantee.)
+// ---------------------------------------------------------------------------
 template <class V>
-__device__ __forceinline__ double path_dist(const V &v, double u, double px, double py)
-{
-    double x, y;
-    path_eval(v, u, x, y);
-    const double dx = S::sub(x, px), dy = S::sub(y, py);
-    return S::sqrt(S::fma(dy, dy, S::mul(dx, dx)));
-}
+struct PathCursor {
+    const V &v;
+    int N;
+    double us0, us1, last_start;
+    int kind;
+    double lo, hi, un1, len;
+    double2 a1, b1, c1, a2, b2, c2;
+
+    __device__ __forceinline__ explicit PathCursor(const V &v_) : v(v_), N(v_.n_wps()), kind(-1)
+    {
+        us0 = v.us(0); us1 = v.us(1);
+        last_start = S::sub(v.us(N - 2), 0.001);
+        lo = hi = un1 = len = 0.0;
+        a1 = b1 = c1 = a2 = b2 = c2 = make_double2(0.0, 0.0);
+    }
+
+    __device__ __forceinline__ bool hit(double u) const
+    {
+        if (kind == 2) return (u > lo) && (u <= hi) && (u < last_start);
+        if (kind == 0) return (u >= us0) && (u <= us1);
+        if (kind == 1) return (u >= last_start);
+        if (kind == 3) return (u < us0);
+        return false;
+    }
+
+    __device__ __forceinline__ void locate(double u)
+    {
+        const int rows = N - 2;
+        if (u >= us0 && u <= us1) {
+            kind = 0;
+            a2 = v.pa(0); b2 = v.pb(0); c2 = v.pc(0);
+        } else if (u >= last_start) {
+            kind = 1;
+            a2 = v.pa(rows - 1); b2 = v.pb(rows - 1); c2 = v.pc(rows - 1);
+        } else {
+            const int n = u_index(v, u, N);
+            kind = (n == 0) ? 3 : 2;
+            lo = v.us(n); hi = v.us(n + 1);
+            un1 = hi;
+            len = S::sub(hi, lo);
+            const int r1 = (n - 1 < 0) ? rows - 1 : n - 1;
+            a1 = v.pa(r1); b1 = v.pb(r1); c1 = v.pc(r1);
+            a2 = v.pa(n); b2 = v.pb(n); c2 = v.pc(n);
+        }
+    }
+
+    __device__ __forceinline__ void eval(double u, double &x, double &y)
+    {
+        if (!hit(u)) locate(u);
+        const double uu = S::mul(u, u);
+        const double x2 = poly2(a2.x, b2.x, c2.x, u, uu), y2 = poly2(a2.y, b2.y, c2.y, u, uu);
+        if (kind <= 1) { x = x2; y = y2; return; }
+        const double mu_r = S::div(S::sub(u, lo), len);
+        const double mu_f = S::div(S::sub(un1, u), len);
+        const double x1 = poly2(a1.x, b1.x, c1.x, u, uu), y1 = poly2(a1.y, b1.y, c1.y, u, uu);
+        x = S::add(S::mul(mu_r, x2), S::mul(mu_f, x1));
+        y = S::add(S::mul(mu_r, y2), S::mul(mu_f, y1));
+    }
+
+    // np.linalg.norm(path(u) - pos) (predef_path.py:246): sqrt(x.dot(x)) with BLAS
+    // ddot's fused accumulate -> sqrt(fma(dy, dy, dx*dx)).
+    __device__ __forceinline__ double dist(double u, double px, double py)
+    {
+        double x, y;
+        eval(u, x, y);
+        const double dx = S::sub(x, px), dy = S::sub(y, py);
+        return S::sqrt(S::fma(dy, dy, S::mul(dx, dx)));
+    }
+};
 
 // QPMI2D.get_closest_u (predef_path.py:226-248) = scipy fminbound = bounded Brent
 // (_minimize_scalar_bounded, scipy/optimize/_optimize.py:2289-2440) on
 // [-10, L+10], xatol = 1e-6, maxfun = 500.  Literal restatement; every lane runs
 // its own iteration count (mean ~15, max ~47).
 template <class V>
-__device__ double closest_u(const V &v, double px, double py, int &nfev)
+__device__ __forceinline__ double closest_u(PathCursor<V> &pc, double px, double py, int &nfev)
 {
+    const V &v = pc.v;
     const double xatol = 1e-6;
     const int maxfun = 500;
     const double sqrt_eps = 1.4832396974191326e-08;      // sqrt(2.2e-16)
@@ -272,7 +349,7 @@ __device__ double closest_u(const V &v, double px, double py, int &nfev)
     double nfc = fulc, xf = fulc;
     double rat = 0.0, e = 0.0;
     double x = xf;
-    double fx = path_dist(v, x, px, py);
+    double fx = pc.dist(x, px, py);
     int num = 1;
     double fu;
     double ffulc = fx, fnfc = fx;
@@ -311,7 +388,7 @@ __device__ double closest_u(const V &v, double px, double py, int &nfev)
         }
         const double si = (double)((rat > 0.0) - (rat < 0.0)) + (rat == 0.0 ? 1.0 : 0.0);
         x = S::add(xf, S::mul(si, fmax(fabs(rat), tol1)));
-        fu = path_dist(v, x, px, py);
+        fu = pc.dist(x, px, py);
         num += 1;
 
         if (fu <= fx) {
@@ -365,7 +442,9 @@ __device__ __forceinline__ void load_state(const D2dParams &p, int64_t i, EnvSta
     s.steps = m.x; s.flags = m.y; s.episode = m.z; s.n_obs = m.w;
 }
 
-__device__ __forceinline__ void store_state(const D2dParams &p, int64_t i, const EnvState &s)
+// Bodies and impulses are final right after the solver: they are stored at once so
+// that their ~60 registers are free during the observation / closest-point search.
+__device__ __forceinline__ void store_bodies(const D2dParams &p, int64_t i, const EnvState &s)
 {
 #pragma unroll
     for (int b = 0; b < 3; b++) {
@@ -375,8 +454,18 @@ __device__ __forceinline__ void store_state(const D2dParams &p, int64_t i, const
     }
 #pragma unroll
     for (int j = 0; j < 6; j++) p.jacc[j * p.np + i] = make_double2(s.jx[j], s.jy[j]);
+}
+
+__device__ __forceinline__ void store_scalars(const D2dParams &p, int64_t i, const EnvState &s)
+{
     p.acc[i] = make_double2(s.path_error, s.total_reward);
     p.meta[i] = make_int4(s.steps, s.flags, s.episode, s.n_obs);
+}
+
+__device__ __forceinline__ void store_state(const D2dParams &p, int64_t i, const EnvState &s)
+{
+    store_bodies(p, i, s);
+    store_scalars(p, i, s);
 }
 
 // Drone.__init__ (Drone.py:9-95): three bodies at rest, impulses cleared.
@@ -432,25 +521,36 @@ __device__ __forceinline__ void physics_step(EnvState &s, const D2dConst &c, dou
     }
     rc0 = rc[0]; rs0 = rs[0];
 
-    // 4. cpPivotJoint preStep.  Anchors lie on the body x axis, so
-    //    r1 = Rot(a_motor) * (ax, 0) = (c*ax, s*ax) and r2 = (c0*bx, s0*bx).
-    double r1x[6], r1y[6], r2x[6], r2y[6], k11[6], k12[6], k22[6], bsx[6], bsy[6];
+    // 4. cpPivotJoint preStep.  Anchors lie on the body x axis, so r1 = Rot(a_motor)*(ax, 0)
+    //    = ax*(c, s) and r2 = bx*(c0, s0) with ax in {-d, 0, +d}, bx in {-(R+d), -R, -(R-d), R-d, R, R+d}.
+    //    Negating an anchor negates r exactly, so only 2 motor vectors and 3 frame vectors are kept;
+    //    joint j uses  r1 = S1[j] * q1[motor],  r2 = S2[j] * q2[Q2[j]]  (signs folded into the FMAs).
+    //      j:        0 (L1)  1 (L2)  2 (L3)  3 (R1)  4 (R2)  5 (R3)
+    //      r1:       -q1[L]    0     +q1[L]  -q1[R]    0     +q1[R]        q1[m] = d*(c_m, s_m)
+    //      r2:       -q2[2]  -q2[1]  -q2[0]  +q2[0]  +q2[1]  +q2[2]        q2 = {R-d, R, R+d}*(c0, s0)
+    double q1x[2], q1y[2], q2x[3], q2y[3];
+    q1x[0] = rc[1] * c.d; q1y[0] = rs[1] * c.d; q1x[1] = rc[2] * c.d; q1y[1] = rs[2] * c.d;
+    q2x[0] = rc[0] * (c.R - c.d); q2y[0] = rs[0] * (c.R - c.d);
+    q2x[1] = rc[0] * c.R; q2y[1] = rs[0] * c.R;
+    q2x[2] = rc[0] * (c.R + c.d); q2y[2] = rs[0] * (c.R + c.d);
+    double k11[6], k12[6], k22[6], bsx[6], bsy[6];
 #pragma unroll
     for (int j = 0; j < 6; j++) {
         const int m = (j < 3) ? 1 : 2;
-        const double ax = (double)((j % 3) - 1) * c.d;                        // -d, 0, +d (Drone.py:61-95)
-        const double bx = ((j < 3) ? -c.R : c.R) + ax;
-        r1x[j] = rc[m] * ax; r1y[j] = rs[m] * ax;
-        r2x[j] = rc[0] * bx; r2y[j] = rs[0] * bx;
+        const double s1 = (double)((j % 3) - 1);                 // -1, 0, +1
+        const double s2 = (j < 3) ? -1.0 : 1.0;
+        const int qi = (j < 3) ? 2 - j : j - 3;
+        const double r1x = s1 * q1x[m - 1], r1y = s1 * q1y[m - 1];
+        const double r2x = s2 * q2x[qi], r2y = s2 * q2y[qi];
         // k_tensor(a = motor, b = frame)
         double a11 = c.msum, a12 = 0.0, a22 = c.msum;
-        a11 += r1y[j] * r1y[j] * c.iinv_m; a12 += -r1x[j] * r1y[j] * c.iinv_m; a22 += r1x[j] * r1x[j] * c.iinv_m;
-        a11 += r2y[j] * r2y[j] * c.iinv_f; a12 += -r2x[j] * r2y[j] * c.iinv_f; a22 += r2x[j] * r2x[j] * c.iinv_f;
+        a11 += r1y * r1y * c.iinv_m; a12 += -r1x * r1y * c.iinv_m; a22 += r1x * r1x * c.iinv_m;
+        a11 += r2y * r2y * c.iinv_f; a12 += -r2x * r2y * c.iinv_f; a22 += r2x * r2x * c.iinv_f;
         const double det_inv = 1.0 / (a11 * a22 - a12 * a12);
         k11[j] = a22 * det_inv; k12[j] = -a12 * det_inv; k22[j] = a11 * det_inv;
         // bias = -delta / dt (error_bias = 0 -> bias_coef = 1)
-        bsx[j] = ((s.px[0] + r2x[j]) - (s.px[m] + r1x[j])) * c.bias_coef;
-        bsy[j] = ((s.py[0] + r2y[j]) - (s.py[m] + r1y[j])) * c.bias_coef;
+        bsx[j] = ((s.px[0] + r2x) - (s.px[m] + r1x)) * c.bias_coef;
+        bsy[j] = ((s.py[0] + r2y) - (s.py[m] + r1y)) * c.bias_coef;
     }
 
     // 5. cpBodyUpdateVelocity (space damping 1; env:376-380 has no physical effect)
@@ -467,21 +567,32 @@ __device__ __forceinline__ void physics_step(EnvState &s, const D2dConst &c, dou
 #pragma unroll
     for (int j = 0; j < 6; j++) {
         const int m = (j < 3) ? 1 : 2;
+        const double s1 = (double)((j % 3) - 1), s2 = (j < 3) ? -1.0 : 1.0;
+        const int qi = (j < 3) ? 2 - j : j - 3;
         const double jx = s.jx[j], jy = s.jy[j];
         s.vx[m] -= jx * c.minv_m; s.vy[m] -= jy * c.minv_m;
-        s.om[m] -= c.iinv_m * (r1x[j] * jy - r1y[j] * jx);
+        if (j % 3 != 1) s.om[m] -= c.iinv_m * (s1 * q1x[m - 1] * jy - s1 * q1y[m - 1] * jx);
         s.vx[0] += jx * c.minv_f; s.vy[0] += jy * c.minv_f;
-        s.om[0] += c.iinv_f * (r2x[j] * jy - r2y[j] * jx);
+        s.om[0] += c.iinv_f * (s2 * q2x[qi] * jy - s2 * q2y[qi] * jx);
     }
 
-    // 7. sequential impulses: iterations x 6 joints, Gauss-Seidel order left_1..right_3
+    // 7. sequential impulses: iterations x 6 joints, Gauss-Seidel order left_1..right_3.
+    //    The centre joints (r1 = 0) exert no torque on the motor (adding +-0 is exact).
 #pragma unroll 1
     for (int it = 0; it < c.iterations; it++) {
 #pragma unroll
         for (int j = 0; j < 6; j++) {
             const int m = (j < 3) ? 1 : 2;
-            const double vrx = (s.vx[0] - r2y[j] * s.om[0]) - (s.vx[m] - r1y[j] * s.om[m]);
-            const double vry = (s.vy[0] + r2x[j] * s.om[0]) - (s.vy[m] + r1x[j] * s.om[m]);
+            const double s1 = (double)((j % 3) - 1), s2 = (j < 3) ? -1.0 : 1.0;
+            const int qi = (j < 3) ? 2 - j : j - 3;
+            const double r2x = s2 * q2x[qi], r2y = s2 * q2y[qi];
+            double vax = s.vx[m], vay = s.vy[m];
+            if (j % 3 != 1) {
+                vax = s.vx[m] - s1 * q1y[m - 1] * s.om[m];
+                vay = s.vy[m] + s1 * q1x[m - 1] * s.om[m];
+            }
+            const double vrx = (s.vx[0] - r2y * s.om[0]) - vax;
+            const double vry = (s.vy[0] + r2x * s.om[0]) - vay;
             const double ex = bsx[j] - vrx, ey = bsy[j] - vry;
             double jx = ex * k11[j] + ey * k12[j];
             double jy = ex * k12[j] + ey * k22[j];
@@ -489,9 +600,9 @@ __device__ __forceinline__ void physics_step(EnvState &s, const D2dConst &c, dou
             s.jx[j] = ox + jx; s.jy[j] = oy + jy;          // clamp to maxForce*dt = inf is a no-op
             jx = s.jx[j] - ox; jy = s.jy[j] - oy;
             s.vx[m] -= jx * c.minv_m; s.vy[m] -= jy * c.minv_m;
-            s.om[m] -= c.iinv_m * (r1x[j] * jy - r1y[j] * jx);
+            if (j % 3 != 1) s.om[m] -= c.iinv_m * (s1 * q1x[m - 1] * jy - s1 * q1y[m - 1] * jx);
             s.vx[0] += jx * c.minv_f; s.vy[0] += jy * c.minv_f;
-            s.om[0] += c.iinv_f * (r2x[j] * jy - r2y[j] * jx);
+            s.om[0] += c.iinv_f * (r2x * jy - r2y * jx);
         }
     }
 }
@@ -607,9 +718,10 @@ __device__ __forceinline__ void observe(const V &v, const D2dConst &c, EnvState 
     // env:730-734.  The reference runs the identical fminbound a second time at
     // env:737; same arguments -> same result, evaluated once.
     int nfev;
-    const double u = closest_u(v, x, y, nfev);
+    PathCursor<V> pc(v);
+    const double u = closest_u(pc, x, y, nfev);
     double cx, cy;
-    path_eval(v, u, cx, cy);
+    pc.eval(u, cx, cy);
     ax.o19 = m1to1(cx, 0.0, W); ax.o20 = m1to1(cy, 0.0, H);
     put(19, ax.o19); put(20, ax.o20);
     ax.u_star = u; ax.nfev = nfev;
@@ -618,7 +730,7 @@ __device__ __forceinline__ void observe(const V &v, const D2dConst &c, EnvState 
     const double L = v.us(v.n_wps() - 1);
     const double u_la = (S::add(u, c.lookahead) > L) ? L : S::add(u, c.lookahead);
     double lx, ly;
-    path_eval(v, u_la, lx, ly);
+    pc.eval(u_la, lx, ly);
     if (fabs(lx - tgt.x) < 10.0 && fabs(ly - tgt.y) < 10.0) s.flags |= D2D_F_LATCHED;
     if (s.flags & D2D_F_LATCHED) { lx = tgt.x; ly = tgt.y; }
     put(21, m1to1(lx, 0.0, W)); put(22, m1to1(ly, 0.0, H));
@@ -736,20 +848,29 @@ __device__ __forceinline__ int sample_obstacles(const D2dParams &p, EnvView &ev,
         const double size = rng.uniform(10.0, 50.0);
         const double ddx = ox - x, ddy = oy - y;
         if (on_path) {
-            p.obxy[(int64_t)slot * p.np + ev.i] = make_double2(x, y);
-            p.obr[(int64_t)slot * p.np + ev.i] = size;
+            p.obxy[ev.orow(slot)] = make_double2(x, y);
+            p.obr[ev.orow(slot)] = size;
             slot++; made++;
         } else if (sqrt(ddx * ddx + ddy * ddy) > size + 10.0) {
-            p.obxy[(int64_t)slot * p.np + ev.i] = make_double2(ox, oy);
-            p.obr[(int64_t)slot * p.np + ev.i] = size;
+            p.obxy[ev.orow(slot)] = make_double2(ox, oy);
+            p.obr[ev.orow(slot)] = size;
             slot++; made++;
         }
     }
     return slot;
 }
 
+// Samples episode `episode` of env i: writes its per-env tables into table buffer `par`
+// (curriculum mode) and returns the spawn pose + obstacle count.  Pure function of
+// (seed, global env id, episode): whoever computes it -- a refill warp ahead of time, the
+// reset kernel, or the owning lane as a fallback -- gets the same episode.
+struct ResetOut {
+    double x, y, angle;
+    int n_obs;
+};
+
 template <bool PER_ENV>
-__device__ __noinline__ void reset_env(const D2dParams &p, int64_t i, EnvState &s, int episode)
+__device__ __noinline__ ResetOut reset_env(const D2dParams &p, int64_t i, int episode, int par)
 {
     const D2dConst &c = p.c;
     ResetRng rng((uint32_t)(c.env_id_base + i), (uint32_t)episode, c.seed_lo, c.seed_hi);
@@ -758,12 +879,10 @@ __device__ __noinline__ void reset_env(const D2dParams &p, int64_t i, EnvState &
         const double x = rng.uniform(c.sp_xmin, c.sp_xmax);
         const double y = rng.uniform(c.sp_ymin, c.sp_ymax);
         const double a = rng.uniform(-D2D_PI / 4, D2D_PI / 4);
-        spawn(s, c, x, y, a);
-        s.episode = episode;
-        s.n_obs = 0;
-        return;
+        return ResetOut{x, y, a, 0};
     }
     // ---- curriculum: random path (predef_path.py:307-363) ----
+    EnvView ev{&p, i, 0, par};
     const int N = c.n_wps;
     int corner = 2;                                              // 'DR' when random_path_spawn is False (env:214)
     if (c.random_path_spawn) corner = rng.randint(c.corner_lo, c.corner_hi);   // 1 DL, 2 DR, 3 UL, 4 UR (env:202-211)
@@ -781,8 +900,8 @@ __device__ __noinline__ void reset_env(const D2dParams &p, int64_t i, EnvState &
     // the reference inverts the 3x3 Vandermonde matrix -- same polynomial).
     double u_prev2 = 0.0, u_prev = 0.0, u_cur = 0.0;
     double xa = 0.0, ya = 0.0, xb = wx, yb = wy;                  // waypoints k-2, k-1
-    p.wps[i] = make_double2(wx, wy);
-    p.us[i] = 0.0;
+    p.wps[ev.wrow(0)] = make_double2(wx, wy);
+    p.us[ev.wrow(0)] = 0.0;
     for (int k = 1; k < N; k++) {
         const double az = rng.uniform(az_lo, az_hi);
         double sn, cs;
@@ -790,8 +909,8 @@ __device__ __noinline__ void reset_env(const D2dParams &p, int64_t i, EnvState &
         const double nx = xb + c.seg_len * cs, ny = yb + c.seg_len * sn;
         const double ddx = nx - xb, ddy = ny - yb;
         u_cur = u_prev + sqrt(ddx * ddx + ddy * ddy);
-        p.wps[(int64_t)k * p.np + i] = make_double2(nx, ny);
-        p.us[(int64_t)k * p.np + i] = u_cur;
+        p.wps[ev.wrow(k)] = make_double2(nx, ny);
+        p.us[ev.wrow(k)] = u_cur;
         if (k >= 2) {
             const double u0 = u_prev2, u1 = u_prev, u2 = u_cur;
             const double dx01 = (xb - xa) / (u1 - u0), dx12 = (nx - xb) / (u2 - u1);
@@ -799,17 +918,15 @@ __device__ __noinline__ void reset_env(const D2dParams &p, int64_t i, EnvState &
             const double axx = (dx12 - dx01) / (u2 - u0), ayy = (dy12 - dy01) / (u2 - u0);
             const double bxx = dx01 - axx * (u0 + u1), byy = dy01 - ayy * (u0 + u1);
             const double cxx = xa - axx * u0 * u0 - bxx * u0, cyy = ya - ayy * u0 * u0 - byy * u0;
-            const int64_t r = (int64_t)(k - 2) * p.np + i;
-            p.pa[r] = make_double2(axx, ayy);
-            p.pb[r] = make_double2(bxx, byy);
-            p.pc[r] = make_double2(cxx, cyy);
+            p.pa[ev.wrow(k - 2)] = make_double2(axx, ayy);
+            p.pb[ev.wrow(k - 2)] = make_double2(bxx, byy);
+            p.pc[ev.wrow(k - 2)] = make_double2(cxx, cyy);
         }
         xa = xb; ya = yb; xb = nx; yb = ny;
         u_prev2 = u_prev; u_prev = u_cur;
     }
     double sx = x0, sy = y0;                                      // env:320-321
     const double sa = rng.uniform(-D2D_PI / 4, D2D_PI / 4);       // env:322
-    EnvView ev{&p, i, 0};
     int n_obs = 0;
     if (c.stage == 2) {                                           // env:329-333
         sx = rng.uniform(100.0, c.W - 100.0);
@@ -830,9 +947,7 @@ __device__ __noinline__ void reset_env(const D2dParams &p, int64_t i, EnvState &
             n_obs = sample_obstacles(p, ev, rng, n_obs, 1, 0.0, 0.0, true);
         }
     }
-    spawn(s, c, sx, sy, sa);
-    s.episode = episode;
-    s.n_obs = n_obs;
+    return ResetOut{sx, sy, sa, n_obs};
 }
 
 }  // namespace d2d

@@ -13,12 +13,28 @@
 //   meta [N]    int4     (step counter, flags, episode number, n_obs)
 //   last [N]    double4-ish record of the last finished episode (2 x double2)
 //
+// Prefetched next episode ("staging slot", one per env): the re-spawn of env i
+// for episode k+1 is a pure function of (seed, global env id, k+1), so it is
+// computed ahead of time by dedicated refill warps of the step kernel and only
+// swapped in when episode k ends (no sampling / closest-point search on the
+// step's critical path):
+//   stg_xy  [N] double2 (x, y)   stg_an [N] double2 (angle, unused)
+//   stg_meta[N] int4    (episode the slot holds, n_obs, look-ahead latch, 0)
+//   stg_obs [N][27] float        first observation of the staged episode
+//   queue [2][3][N] int32 + qcount[2][3]: two-stage refill pipeline.  Envs whose slot was
+//   consumed in step t are appended to queue A[t % 3]; the "sample" refill blocks of step
+//   t+1 draw the episode (tables + spawn pose) and append to queue B[(t+1) % 3]; the
+//   "observe" refill blocks of step t+2 compute its first observation and publish the
+//   slot.  Each stage is shorter than the main lanes' step, so prefetching never extends
+//   the kernel; a slot that is not ready when needed falls back to in-lane sampling.
+//
 // Per-env tables (curriculum mode only; rows of waypoint/segment index major so
-// that lanes reading the same row coalesce):
-//   us   [MAX_WPS][N]        double
-//   wps  [MAX_WPS][N]        double2 (x, y)
-//   pa/pb/pc [MAX_WPS][N]    double2 (ax, ay) (bx, by) (cx, cy)   QPMI2D rows
-//   obxy [MAX_OBS_ENV][N]    double2 ; obr [MAX_OBS_ENV][N] double
+// that lanes reading the same row coalesce).  Two buffers per env: the live
+// episode and the staged one (meta flag D2D_F_PARITY selects the live buffer):
+//   us   [2][MAX_WPS][N]        double
+//   wps  [2][MAX_WPS][N]        double2 (x, y)
+//   pa/pb/pc [2][MAX_WPS][N]    double2 (ax, ay) (bx, by) (cx, cy)   QPMI2D rows
+//   obxy [2][MAX_OBS_ENV][N]    double2 ; obr [2][MAX_OBS_ENV][N] double
 #pragma once
 #include <stddef.h>
 #include <stdint.h>
@@ -35,6 +51,7 @@ struct D2dLayout {
     int64_t n;          // environments
     int64_t np;         // padded to a multiple of 32 (row stride)
     size_t off_pos, off_vel, off_ang, off_jacc, off_acc, off_meta, off_last;
+    size_t off_stg_xy, off_stg_an, off_stg_meta, off_stg_obs, off_queue, off_qcount;
     size_t off_us, off_wps, off_pa, off_pb, off_pc, off_obxy, off_obr;
     size_t bytes;
     int per_env_tables;
@@ -56,15 +73,21 @@ static inline void d2d_make_layout(D2dLayout *L, int64_t n, int per_env_tables)
     L->off_acc = take(np * 16);
     L->off_meta = take(np * 16);
     L->off_last = take(2 * np * 16);
+    L->off_stg_xy = take(np * 16);
+    L->off_stg_an = take(np * 16);
+    L->off_stg_meta = take(np * 16);
+    L->off_stg_obs = take(np * D2D_OBS_DIM * 4);
+    L->off_queue = take(3 * 3 * np * 4);       // A[3][np], B env[3][np], B target episode[3][np]
+    L->off_qcount = take(256);
     L->off_us = L->off_wps = L->off_pa = L->off_pb = L->off_pc = L->off_obxy = L->off_obr = 0;
     if (per_env_tables) {
-        L->off_us = take((size_t)D2D_MAX_WPS * np * 8);
-        L->off_wps = take((size_t)D2D_MAX_WPS * np * 16);
-        L->off_pa = take((size_t)D2D_MAX_WPS * np * 16);
-        L->off_pb = take((size_t)D2D_MAX_WPS * np * 16);
-        L->off_pc = take((size_t)D2D_MAX_WPS * np * 16);
-        L->off_obxy = take((size_t)D2D_MAX_OBS_ENV * np * 16);
-        L->off_obr = take((size_t)D2D_MAX_OBS_ENV * np * 8);
+        L->off_us = take((size_t)2 * D2D_MAX_WPS * np * 8);
+        L->off_wps = take((size_t)2 * D2D_MAX_WPS * np * 16);
+        L->off_pa = take((size_t)2 * D2D_MAX_WPS * np * 16);
+        L->off_pb = take((size_t)2 * D2D_MAX_WPS * np * 16);
+        L->off_pc = take((size_t)2 * D2D_MAX_WPS * np * 16);
+        L->off_obxy = take((size_t)2 * D2D_MAX_OBS_ENV * np * 16);
+        L->off_obr = take((size_t)2 * D2D_MAX_OBS_ENV * np * 8);
     }
     L->bytes = o;
 }
@@ -74,6 +97,7 @@ static inline void d2d_make_layout(D2dLayout *L, int64_t n, int per_env_tables)
 #define D2D_F_LATCHED 2
 #define D2D_F_DONE 4      // terminal state kept (auto_reset == 0)
 #define D2D_F_INIT 8      // spawned at least once (episode counter valid)
+#define D2D_F_PARITY 16   // which of the two per-env table buffers holds the live episode
 
 // One shared scenario (test mode): path + circles, read-only, staged into shared memory.
 struct D2dSharedTables {
@@ -113,6 +137,11 @@ struct D2dParams {
     double *us;
     double2 *wps, *pa, *pb, *pc, *obxy;
     double *obr;
+    double2 *stg_xy, *stg_an;
+    int4 *stg_meta;
+    float *stg_obs;
+    int *queue, *qcount;
+    int refill_blocks;         // leading blocks of the step grid that prefetch episodes (per stage)
     const D2dSharedTables *shared;
     // I/O of one step
     const float *actions;

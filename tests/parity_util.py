@@ -101,7 +101,8 @@ def run_parity(pkg, mode, scenario, n_envs, n_steps, seed=0, action_scale=1.0, i
     age = np.zeros(n_envs, dtype=int)                   # steps since both sides were last identical
     R = dict(max_state_err=0.0, max_state_err_1step=0.0, max_obs_core_err=0.0, max_obs_path_err=0.0,
              max_u_err=0.0, max_reward_err=0.0, flag_mismatch=0, nearest_mismatch=0, nfev_mismatch=0,
-             u_gt_1e9=0, env_steps=0, episodes=0, max_f32_obs_err=0.0, max_ape_err=0.0)
+             u_gt_1e9=0, env_steps=0, episodes=0, max_f32_obs_err=0.0, max_ape_err=0.0, max_reset_obs_err=0.0,
+             reset_obs_checked=0)
     for t in range(n_steps):
         actions = (rng.uniform(-1, 1, (n_envs, 2)) * action_scale).astype(np.float32)
         env.step_device(torch.from_numpy(actions).to(env.device))
@@ -163,6 +164,20 @@ def run_parity(pkg, mode, scenario, n_envs, n_steps, seed=0, action_scale=1.0, i
                 age[i] = 0
                 if per_env:
                     paths[i], obsts[i] = np_[i], no_[i]
+                if g_done[i]:
+                    # the observation returned at a done step is the first observation of the NEW episode
+                    # (env.reset() -> get_observation(), env:908-912): check it against the oracle
+                    out0 = oracle.StepOut()
+                    pth, obt = (paths[i], obsts[i]) if per_env else (path, obst)
+                    oracle.lib().d2o_observe(C.byref(states[i]), C.byref(pth), C.byref(obt), C.byref(cfg), C.byref(out0))
+                    ref0 = np.array(out0.obs[:])
+                    dist = max(np.hypot(out0.closest_x - states[i].body[0].px, out0.closest_y - states[i].body[0].py), 1e-3)
+                    tol_ang = np.zeros(27)
+                    tol_ang[25:27] = 2 * TOL_U / dist      # bearing of the closest point: ill-conditioned near the path
+                    tol_ang[23:25] = 2 * TOL_U / 100.0
+                    err = np.abs(g_obs32[i].astype(np.float64) - ref0) - tol_ang
+                    R["max_reset_obs_err"] = max(R["max_reset_obs_err"], float(err.max()))
+                    R["reset_obs_checked"] += 1
     R["launches"] = env.launch_count
     env.close()
     return {k: (float(v) if isinstance(v, (np.floating, float)) else int(v)) for k, v in R.items()}
