@@ -12,13 +12,6 @@
 
 #include "drone2d_device.cuh"
 
-#ifndef D2D_BLOCK
-#define D2D_BLOCK 128
-#endif
-#ifndef D2D_MIN_BLOCKS
-#define D2D_MIN_BLOCKS 4
-#endif
-
 using namespace d2d;
 
 // ===========================================================================
@@ -30,15 +23,17 @@ struct ViewOf;
 template <>
 struct ViewOf<true> {
     typedef EnvView type;
-    static __device__ __forceinline__ EnvView make(const D2dParams &p, const D2dSharedTables *, int64_t i, int n_obs, int par)
+    static __device__ __forceinline__ EnvView make(const D2dParams &p, const D2dSharedTables *, int64_t i, int n_obs, int par,
+                                                   const double *us_s = nullptr)
     {
-        return EnvView{&p, i, n_obs, par};
+        return EnvView{&p, i, n_obs, par, us_s};
     }
 };
 template <>
 struct ViewOf<false> {
     typedef SharedView type;
-    static __device__ __forceinline__ SharedView make(const D2dParams &, const D2dSharedTables *t, int64_t, int, int)
+    static __device__ __forceinline__ SharedView make(const D2dParams &, const D2dSharedTables *t, int64_t, int, int,
+                                                      const double * = nullptr)
     {
         return SharedView{t};
     }
@@ -58,7 +53,7 @@ __device__ __forceinline__ void stage_shared_tables(const D2dParams &p, D2dShare
 template <bool PER_ENV>
 __device__ __noinline__ int first_observation(const D2dParams &p, const D2dSharedTables *tab, int64_t i, double x,
                                               double y, double angle, int n_obs, int par, float *row, double *o64,
-                                              double *info, int episode)
+                                              double *info, int episode, double2 *coef)
 {
     EnvState s;
     s.px[0] = x; s.py[0] = y; s.an[0] = angle; s.vx[0] = 0.0; s.vy[0] = 0.0; s.om[0] = 0.0;
@@ -73,7 +68,7 @@ __device__ __noinline__ int first_observation(const D2dParams &p, const D2dShare
         if (o64) o64[j] = val;
     };
     ObsAux ax;
-    observe(v, p.c, s, rc0, rs0, nr, put, ax);
+    observe(v, p.c, s, rc0, rs0, nr, put, ax, coef);
     if (info) {
         for (int k = 0; k < D2D_INFO_DOUBLES; k++) info[k] = 0.0;
         info[12] = ax.u_star; info[13] = (double)ax.nfev; info[14] = (double)ax.near_packed; info[15] = (double)episode;
@@ -98,7 +93,8 @@ __device__ __forceinline__ void stage_sample(const D2dParams &p, int64_t e)
 }
 
 template <bool PER_ENV>
-__device__ __forceinline__ void stage_observe(const D2dParams &p, const D2dSharedTables *tab, int64_t e, int target)
+__device__ __forceinline__ void stage_observe(const D2dParams &p, const D2dSharedTables *tab, int64_t e, int target,
+                                              double2 *coef)
 {
     const int4 sm = p.stg_meta[e];
     const int par = sm.z;
@@ -106,7 +102,7 @@ __device__ __forceinline__ void stage_observe(const D2dParams &p, const D2dShare
     if (sm.w != target || sm.x != -1 || p.meta[e].z + 1 != target) return;
     const double2 xy = p.stg_xy[e];
     const int latch = first_observation<PER_ENV>(p, tab, e, xy.x, xy.y, p.stg_an[e].x, sm.y, par,
-                                                 p.stg_obs + e * D2D_OBS_DIM, nullptr, nullptr, target);
+                                                 p.stg_obs + e * D2D_OBS_DIM, nullptr, nullptr, target, coef);
     __threadfence();
     p.stg_meta[e] = make_int4(target, sm.y, latch, target);
 }
@@ -127,6 +123,8 @@ __global__ void __launch_bounds__(D2D_BLOCK, D2D_MIN_BLOCKS) d2d_step_kernel(con
     __shared__ double s_stats[D2D_STATS_DOUBLES];
     __shared__ int s_any_done;
     __shared__ D2dSharedTables s_tab;
+    __shared__ double s_us[PER_ENV ? D2D_MAX_WPS * D2D_BLOCK : 1];   // lane-private us[] columns
+    __shared__ double2 s_coef[6 * D2D_BLOCK];                        // lane-private polynomial rows (PathCursor)
 
     const int tid = threadIdx.x;
     const D2dConst &c = p.c;
@@ -138,14 +136,18 @@ __global__ void __launch_bounds__(D2D_BLOCK, D2D_MIN_BLOCKS) d2d_step_kernel(con
     if (blockIdx.x == 0 && tid == 0) { p.qcount[q_clear] = 0; p.qcount[3 + q_clear] = 0; }
     __syncthreads();
 
+    const long long t_start = clock64();
     int *qa = p.queue, *qb = p.queue + 3 * p.np, *qb_tgt = p.queue + 6 * p.np;
     int *qa_cnt = p.qcount, *qb_cnt = p.qcount + 3;
     if ((int)blockIdx.x < 2 * p.refill_blocks) {
-        const int total = p.refill_blocks * D2D_BLOCK;
-        if ((int)blockIdx.x < p.refill_blocks) {
+        const int total = p.refill_blocks * D2D_BLOCK, n_warps = total / 32;
+        const bool sample_role = (int)blockIdx.x < p.refill_blocks;
+        const int g = (sample_role ? blockIdx.x : blockIdx.x - p.refill_blocks) * D2D_BLOCK + tid;
+        const int first = (g & 31) * n_warps + (g >> 5);        // task dealt to (warp, lane): lane-major over warps
+        if (sample_role) {
             // ---- sample role: queue A of the previous step -> queue B of this step ----
             const int cnt = qa_cnt[q_read];
-            for (int t = blockIdx.x * D2D_BLOCK + tid; t < cnt; t += total) {
+            for (int t = first; t < cnt; t += total) {
                 const int e = qa[(int64_t)q_read * p.np + t];
                 stage_sample<PER_ENV>(p, e);
                 const int slot = atomicAdd(&qb_cnt[q_write], 1);
@@ -155,9 +157,14 @@ __global__ void __launch_bounds__(D2D_BLOCK, D2D_MIN_BLOCKS) d2d_step_kernel(con
         } else {
             // ---- observe role: queue B of the previous step ----
             const int cnt = qb_cnt[q_read];
-            for (int t = (blockIdx.x - p.refill_blocks) * D2D_BLOCK + tid; t < cnt; t += total)
+            for (int t = first; t < cnt; t += total)
                 stage_observe<PER_ENV>(p, &s_tab, (int64_t)qb[(int64_t)q_read * p.np + t],
-                                       qb_tgt[(int64_t)q_read * p.np + t]);
+                                       qb_tgt[(int64_t)q_read * p.np + t], &s_coef[tid]);
+        }
+        if ((tid & 31) == 0 && first < (sample_role ? qa_cnt[q_read] : qb_cnt[q_read])) {
+            const unsigned long long dt = (unsigned long long)(clock64() - t_start);
+            const int r = sample_role ? 1 : 2;
+            atomicMax(&p.role_cycles[r], dt); atomicAdd(&p.role_cycles[8 + r], dt); atomicAdd(&p.role_cycles[16 + r], 1ull);
         }
         return;
     }
@@ -185,10 +192,15 @@ __global__ void __launch_bounds__(D2D_BLOCK, D2D_MIN_BLOCKS) d2d_step_kernel(con
         physics_step(s, c, (double)act.x, (double)act.y, rc0, rs0);
         s.steps += 1;                                               // env:407
         store_bodies(p, i, s);
+        const long long t_phys = clock64();
 
         float *row = &s_obs[tid * D2D_OBS_DIM];
         const int par = (s.flags & D2D_F_PARITY) ? 1 : 0;
-        typename ViewOf<PER_ENV>::type v = ViewOf<PER_ENV>::make(p, &s_tab, i, s.n_obs, par);
+        if (PER_ENV) {
+            const uint32_t base = (uint32_t)(par * D2D_MAX_WPS) * (uint32_t)p.np + (uint32_t)i;
+            for (int k = 0; k < c.n_wps; k++) s_us[k * D2D_BLOCK + tid] = p.us[base + (uint32_t)k * (uint32_t)p.np];
+        }
+        typename ViewOf<PER_ENV>::type v = ViewOf<PER_ENV>::make(p, &s_tab, i, s.n_obs, par, &s_us[tid]);
         Nearest nr;
         const bool hit = scan_obstacles(v, c, s.px[0], s.py[0], rc0, rs0, true, nr);
         if (hit) s.flags |= D2D_F_COLLIDED;                         // begin callback, env:17-19
@@ -199,7 +211,9 @@ __global__ void __launch_bounds__(D2D_BLOCK, D2D_MIN_BLOCKS) d2d_step_kernel(con
             if (o64) o64[j] = val;
         };
         ObsAux ax;
-        observe(v, c, s, rc0, rs0, nr, put, ax);
+        const long long t_scan = clock64();
+        observe(v, c, s, rc0, rs0, nr, put, ax, &s_coef[tid]);
+        const long long t_obs = clock64();
 
         StepResult r;
         reward_and_done(c, s, ax, v.n_obs() > 0, r);
@@ -261,7 +275,8 @@ __global__ void __launch_bounds__(D2D_BLOCK, D2D_MIN_BLOCKS) d2d_step_kernel(con
                     const ResetOut ro = reset_env<PER_ENV>(p, i, next_ep, par);
                     nx = ro.x; ny = ro.y; na = ro.angle; n_obs = ro.n_obs;
                     new_flags = D2D_F_INIT | (par ? D2D_F_PARITY : 0);
-                    new_flags |= first_observation<PER_ENV>(p, &s_tab, i, nx, ny, na, n_obs, par, row, nullptr, nullptr, next_ep);
+                    new_flags |= first_observation<PER_ENV>(p, &s_tab, i, nx, ny, na, n_obs, par, row, nullptr, nullptr,
+                                                            next_ep, &s_coef[tid]);
                 }
                 spawn(s, c, nx, ny, na);
                 s.flags = new_flags; s.episode = next_ep; s.n_obs = n_obs;
@@ -271,6 +286,17 @@ __global__ void __launch_bounds__(D2D_BLOCK, D2D_MIN_BLOCKS) d2d_step_kernel(con
             }
         }
         store_scalars(p, i, s);
+        if ((tid & 31) == 0) {
+            const long long t_end = clock64();
+            const unsigned long long d[7] = {(unsigned long long)(t_end - t_start), 0, 0, (unsigned long long)(t_phys - t_start),
+                                             (unsigned long long)(t_scan - t_phys), (unsigned long long)(t_obs - t_scan),
+                                             (unsigned long long)(t_end - t_obs)};
+#pragma unroll
+            for (int r = 0; r < 7; r++) {
+                if (r == 1 || r == 2) continue;
+                atomicMax(&p.role_cycles[r], d[r]); atomicAdd(&p.role_cycles[8 + r], d[r]); atomicAdd(&p.role_cycles[16 + r], 1ull);
+            }
+        }
     }
     __syncthreads();
 
@@ -296,6 +322,7 @@ template <bool PER_ENV>
 __global__ void __launch_bounds__(D2D_BLOCK) d2d_reset_kernel(const __grid_constant__ D2dParams p)
 {
     __shared__ D2dSharedTables s_tab;
+    __shared__ double2 s_coef[6 * D2D_BLOCK];
     const int tid = threadIdx.x;
     const int64_t i = (int64_t)blockIdx.x * D2D_BLOCK + tid;
     if (!PER_ENV) stage_shared_tables(p, &s_tab, tid, D2D_BLOCK);
@@ -310,20 +337,21 @@ __global__ void __launch_bounds__(D2D_BLOCK) d2d_reset_kernel(const __grid_const
     const int latch = first_observation<PER_ENV>(p, &s_tab, i, ro.x, ro.y, ro.angle, ro.n_obs, par,
                                                  p.obs ? p.obs + i * D2D_OBS_DIM : nullptr,
                                                  p.obs64 ? p.obs64 + i * D2D_OBS_DIM : nullptr,
-                                                 p.info ? p.info + i * D2D_INFO_DOUBLES : nullptr, episode);
+                                                 p.info ? p.info + i * D2D_INFO_DOUBLES : nullptr, episode, &s_coef[tid]);
     EnvState s;
     spawn(s, c, ro.x, ro.y, ro.angle);
     s.flags = D2D_F_INIT | (par ? D2D_F_PARITY : 0) | latch;
     s.episode = episode; s.n_obs = ro.n_obs;
     store_state(p, i, s);
     stage_sample<PER_ENV>(p, i);
-    stage_observe<PER_ENV>(p, &s_tab, i, episode + 1);
+    stage_observe<PER_ENV>(p, &s_tab, i, episode + 1, &s_coef[tid]);
 }
 
 template <bool PER_ENV>
 __global__ void d2d_closest_u_kernel(const __grid_constant__ D2dParams p, const double *pos, double *u_out, int *nfev_out)
 {
     __shared__ D2dSharedTables s_tab;
+    __shared__ double2 s_coef[6 * D2D_BLOCK];
     const int tid = threadIdx.x;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + tid;
     if (!PER_ENV) stage_shared_tables(p, &s_tab, tid, blockDim.x);
@@ -331,8 +359,9 @@ __global__ void d2d_closest_u_kernel(const __grid_constant__ D2dParams p, const 
     if (i >= p.n) return;
     typename ViewOf<PER_ENV>::type v = ViewOf<PER_ENV>::make(p, &s_tab, i, 0, (p.meta[i].y & D2D_F_PARITY) ? 1 : 0);
     int nfev;
-    PathCursor<typename ViewOf<PER_ENV>::type> pc(v);
-    u_out[i] = closest_u(pc, pos[2 * i], pos[2 * i + 1], nfev);
+    PathCursor<typename ViewOf<PER_ENV>::type> pc(v, &s_coef[tid]);
+    double bx, by;
+    u_out[i] = closest_u(pc, pos[2 * i], pos[2 * i + 1], nfev, bx, by);
     nfev_out[i] = nfev;
 }
 
@@ -579,8 +608,11 @@ int d2d_create(const d2d_config *cfg, int64_t n_envs, int64_t env_id_base, uint6
     p.stg_xy = (double2 *)(base + L.off_stg_xy); p.stg_an = (double2 *)(base + L.off_stg_an);
     p.stg_meta = (int4 *)(base + L.off_stg_meta); p.stg_obs = (float *)(base + L.off_stg_obs);
     p.queue = (int *)(base + L.off_queue); p.qcount = (int *)(base + L.off_qcount);
-    // refill capacity: one lane per 32 envs (a larger backlog is handled by striding over the queue)
-    p.refill_blocks = (int)((L.n + 32 * D2D_BLOCK - 1) / (32 * D2D_BLOCK));
+    // refill capacity per stage: one lane per 16 envs (a larger backlog is handled by striding over
+    // the queue).  Tasks are dealt round-robin over the refill WARPS so that each warp carries only
+    // a few lanes: the sampling loops have data-dependent trip counts and a warp runs for the
+    // maximum over its lanes.
+    p.refill_blocks = (int)((L.n + 16 * D2D_BLOCK - 1) / (16 * D2D_BLOCK));
     if (L.per_env_tables) {
         p.us = (double *)(base + L.off_us); p.wps = (double2 *)(base + L.off_wps);
         p.pa = (double2 *)(base + L.off_pa); p.pb = (double2 *)(base + L.off_pb); p.pc = (double2 *)(base + L.off_pc);
@@ -588,8 +620,8 @@ int d2d_create(const d2d_config *cfg, int64_t n_envs, int64_t env_id_base, uint6
     }
     derive_constants(cfg, &p.c, seed, env_id_base);
     cudaError_t err = cudaMalloc(&e->shared_dev, sizeof(D2dSharedTables));
-    if (err == cudaSuccess) err = cudaMalloc(&e->stats_dev, D2D_STATS_DOUBLES * sizeof(double));
-    if (err == cudaSuccess) err = cudaMemset(e->stats_dev, 0, D2D_STATS_DOUBLES * sizeof(double));
+    if (err == cudaSuccess) err = cudaMalloc(&e->stats_dev, (D2D_STATS_DOUBLES + 24) * sizeof(double));
+    if (err == cudaSuccess) err = cudaMemset(e->stats_dev, 0, (D2D_STATS_DOUBLES + 24) * sizeof(double));
     if (err == cudaSuccess) err = cudaMemset(e->shared_dev, 0, sizeof(D2dSharedTables));
     if (err == cudaSuccess) err = cudaMemset(state_dev, 0, L.bytes);
     if (err != cudaSuccess) {
@@ -599,6 +631,7 @@ int d2d_create(const d2d_config *cfg, int64_t n_envs, int64_t env_id_base, uint6
     }
     p.shared = e->shared_dev;
     p.stats = e->stats_dev;
+    p.role_cycles = (unsigned long long *)(e->stats_dev + D2D_STATS_DOUBLES);
     e->tables_set = (cfg->mode == D2D_MODE_CURRICULUM);
     *out = e;
     return D2D_OK;
@@ -830,14 +863,24 @@ int d2d_debug_closest_u(d2d_env *e, const double *pos_dev, double *u_dev, int32_
     if (!e->tables_set) return fail(D2D_ESTATE, "tables not set");
     DeviceGuard guard(e->device);
     cudaStream_t st = (cudaStream_t)stream;
-    const int grid = grid_for(e->p.n, 128);
-    if (e->cfg.mode == D2D_MODE_CURRICULUM) d2d_closest_u_kernel<true><<<grid, 128, 0, st>>>(e->p, pos_dev, u_dev, nfev_dev);
-    else d2d_closest_u_kernel<false><<<grid, 128, 0, st>>>(e->p, pos_dev, u_dev, nfev_dev);
+    const int grid = grid_for(e->p.n, D2D_BLOCK);
+    if (e->cfg.mode == D2D_MODE_CURRICULUM) d2d_closest_u_kernel<true><<<grid, D2D_BLOCK, 0, st>>>(e->p, pos_dev, u_dev, nfev_dev);
+    else d2d_closest_u_kernel<false><<<grid, D2D_BLOCK, 0, st>>>(e->p, pos_dev, u_dev, nfev_dev);
     e->launches++;
     CUDA_TRY(cudaGetLastError());
     return D2D_OK;
 }
 
 int64_t d2d_launch_count(const d2d_env *e) { return e ? e->launches : 0; }
+
+int d2d_debug_role_cycles(d2d_env *e, uint64_t *out24, int reset_after)
+{
+    if (!e || !out24) return fail(D2D_EINVAL, "NULL argument");
+    DeviceGuard guard(e->device);
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaMemcpy(out24, e->p.role_cycles, 24 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    if (reset_after) CUDA_TRY(cudaMemset(e->p.role_cycles, 0, 24 * sizeof(uint64_t)));
+    return D2D_OK;
+}
 
 }  // extern "C"

@@ -22,6 +22,7 @@
 
 #include "drone2d_layout.h"
 
+#define D2D_US_STRIDE D2D_BLOCK   // lane-private shared-memory columns: bank-conflict free for any per-lane index
 #define D2D_PI 3.14159265358979323846
 #define D2D_TWO_PI 6.28318530717958647692
 
@@ -153,12 +154,14 @@ struct EnvView {
     const D2dParams *p;
     int64_t i;
     int nobs;
-    int par;     // table buffer (0/1) this view reads
-    __device__ __forceinline__ int64_t wrow(int k) const { return ((int64_t)(par * D2D_MAX_WPS + k)) * p->np + i; }
-    __device__ __forceinline__ int64_t orow(int k) const { return ((int64_t)(par * D2D_MAX_OBS_ENV + k)) * p->np + i; }
+    int par;                // table buffer (0/1) this view reads
+    const double *us_s;     // optional shared-memory copy of this lane's us[] (element k at us_s[k * D2D_US_STRIDE])
+    // 32-bit element offsets: 2 * 32 rows * np < 2^32 for np < 6.7e7 environments per GPU
+    __device__ __forceinline__ uint32_t wrow(int k) const { return (uint32_t)(par * D2D_MAX_WPS + k) * (uint32_t)p->np + (uint32_t)i; }
+    __device__ __forceinline__ uint32_t orow(int k) const { return (uint32_t)(par * D2D_MAX_OBS_ENV + k) * (uint32_t)p->np + (uint32_t)i; }
     __device__ __forceinline__ int n_wps() const { return p->c.n_wps; }
     __device__ __forceinline__ int n_obs() const { return nobs; }
-    __device__ __forceinline__ double us(int k) const { return p->us[wrow(k)]; }
+    __device__ __forceinline__ double us(int k) const { return us_s ? us_s[k * D2D_US_STRIDE] : p->us[wrow(k)]; }
     __device__ __forceinline__ double2 wp(int k) const { return p->wps[wrow(k)]; }
     __device__ __forceinline__ double2 pa(int r) const { return p->pa[wrow(r)]; }
     __device__ __forceinline__ double2 pb(int r) const { return p->pb[wrow(r)]; }
@@ -266,101 +269,132 @@ struct PathCursor {
     const V &v;
     int N;
     double us0, us1, last_start;
-    int kind;
-    double lo, hi, un1, len;
-    double2 a1, b1, c1, a2, b2, c2;
+    // cached segment: valid for  u > vlo_x  &&  u >= vlo_i  &&  u <= vhi_i  &&  u < vhi_x
+    double vlo_x, vlo_i, vhi_i, vhi_x;
+    bool blend;
+    double lo, un1, len, rlen;
+    // the 2 x 3 polynomial rows of the cached segment live in a lane-private shared-memory
+    // column (coef[r * D2D_BLOCK], r = 0..5 = a1, b1, c1, a2, b2, c2): 24 registers fewer
+    // during the search, 6 conflict-free LDS.128 per evaluation instead.
+    double2 *coef;
 
-    __device__ __forceinline__ explicit PathCursor(const V &v_) : v(v_), N(v_.n_wps()), kind(-1)
+    __device__ __forceinline__ PathCursor(const V &v_, double2 *coef_) : v(v_), N(v_.n_wps()), blend(false), coef(coef_)
     {
         us0 = v.us(0); us1 = v.us(1);
         last_start = S::sub(v.us(N - 2), 0.001);
-        lo = hi = un1 = len = 0.0;
-        a1 = b1 = c1 = a2 = b2 = c2 = make_double2(0.0, 0.0);
+        vlo_x = vlo_i = CUDART_INF; vhi_i = vhi_x = -CUDART_INF;       // empty interval: first use locates
+        lo = un1 = len = rlen = 0.0;
     }
 
     __device__ __forceinline__ bool hit(double u) const
     {
-        if (kind == 2) return (u > lo) && (u <= hi) && (u < last_start);
-        if (kind == 0) return (u >= us0) && (u <= us1);
-        if (kind == 1) return (u >= last_start);
-        if (kind == 3) return (u < us0);
-        return false;
+        return (u > vlo_x) && (u >= vlo_i) && (u <= vhi_i) && (u < vhi_x);
     }
 
     __device__ __forceinline__ void locate(double u)
     {
         const int rows = N - 2;
-        if (u >= us0 && u <= us1) {
-            kind = 0;
-            a2 = v.pa(0); b2 = v.pb(0); c2 = v.pc(0);
-        } else if (u >= last_start) {
-            kind = 1;
-            a2 = v.pa(rows - 1); b2 = v.pb(rows - 1); c2 = v.pc(rows - 1);
+        vlo_x = vlo_i = -CUDART_INF; vhi_i = vhi_x = CUDART_INF;
+        if (u >= us0 && u <= us1) {                                  // first stretch
+            blend = false; vlo_i = us0; vhi_i = us1;
+            coef[3 * D2D_BLOCK] = v.pa(0); coef[4 * D2D_BLOCK] = v.pb(0); coef[5 * D2D_BLOCK] = v.pc(0);
+        } else if (u >= last_start) {                                // last stretch (and beyond the end)
+            blend = false; vlo_i = last_start;
+            coef[3 * D2D_BLOCK] = v.pa(rows - 1); coef[4 * D2D_BLOCK] = v.pb(rows - 1); coef[5 * D2D_BLOCK] = v.pc(rows - 1);
         } else {
             const int n = u_index(v, u, N);
-            kind = (n == 0) ? 3 : 2;
-            lo = v.us(n); hi = v.us(n + 1);
-            un1 = hi;
-            len = S::sub(hi, lo);
-            const int r1 = (n - 1 < 0) ? rows - 1 : n - 1;
-            a1 = v.pa(r1); b1 = v.pb(r1); c1 = v.pc(r1);
-            a2 = v.pa(n); b2 = v.pb(n); c2 = v.pc(n);
+            blend = true;
+            lo = v.us(n); un1 = v.us(n + 1);
+            if (n == 0) { vhi_x = us0; }                             // u < us[0]: rows -1 (= last) and 0
+            else { vlo_x = lo; vhi_i = un1; vhi_x = last_start; }
+            len = S::sub(un1, lo);
+            rlen = S::div(1.0, len);
+            const int r1 = (n - 1 < 0) ? rows - 1 : n - 1;          // Python negative index
+            coef[0] = v.pa(r1); coef[1 * D2D_BLOCK] = v.pb(r1); coef[2 * D2D_BLOCK] = v.pc(r1);
+            coef[3 * D2D_BLOCK] = v.pa(n); coef[4 * D2D_BLOCK] = v.pb(n); coef[5 * D2D_BLOCK] = v.pc(n);
         }
+    }
+
+    // x / len, correctly rounded, from the cached correctly rounded reciprocal (Markstein:
+    // q = RN(x*r), rem = x - len*q exactly (FMA), RN(q + rem*r) = RN(x/len)); bit-identical to
+    // the IEEE division the reference performs, at 3 FMA-class instructions instead of ~12.
+    __device__ __forceinline__ double div_len(double x) const
+    {
+        const double q = S::mul(x, rlen);
+        const double rem = S::fma(-len, q, x);
+        return S::fma(rem, rlen, q);
     }
 
     __device__ __forceinline__ void eval(double u, double &x, double &y)
     {
         if (!hit(u)) locate(u);
         const double uu = S::mul(u, u);
+        const double2 a2 = coef[3 * D2D_BLOCK], b2 = coef[4 * D2D_BLOCK], c2 = coef[5 * D2D_BLOCK];
         const double x2 = poly2(a2.x, b2.x, c2.x, u, uu), y2 = poly2(a2.y, b2.y, c2.y, u, uu);
-        if (kind <= 1) { x = x2; y = y2; return; }
-        const double mu_r = S::div(S::sub(u, lo), len);
-        const double mu_f = S::div(S::sub(un1, u), len);
+        if (!blend) { x = x2; y = y2; return; }
+        const double2 a1 = coef[0], b1 = coef[1 * D2D_BLOCK], c1 = coef[2 * D2D_BLOCK];
+        const double mu_r = div_len(S::sub(u, lo));
+        const double mu_f = div_len(S::sub(un1, u));
         const double x1 = poly2(a1.x, b1.x, c1.x, u, uu), y1 = poly2(a1.y, b1.y, c1.y, u, uu);
         x = S::add(S::mul(mu_r, x2), S::mul(mu_f, x1));
         y = S::add(S::mul(mu_r, y2), S::mul(mu_f, y1));
-    }
-
-    // np.linalg.norm(path(u) - pos) (predef_path.py:246): sqrt(x.dot(x)) with BLAS
-    // ddot's fused accumulate -> sqrt(fma(dy, dy, dx*dx)).
-    __device__ __forceinline__ double dist(double u, double px, double py)
-    {
-        double x, y;
-        eval(u, x, y);
-        const double dx = S::sub(x, px), dy = S::sub(y, py);
-        return S::sqrt(S::fma(dy, dy, S::mul(dx, dx)));
     }
 };
 
 // QPMI2D.get_closest_u (predef_path.py:226-248) = scipy fminbound = bounded Brent
 // (_minimize_scalar_bounded, scipy/optimize/_optimize.py:2289-2440) on
-// [-10, L+10], xatol = 1e-6, maxfun = 500.  Literal restatement; every lane runs
-// its own iteration count (mean ~15, max ~47).
+// [-10, L+10], xatol = 1e-6, maxfun = 500.  Same floating-point operations in the same
+// order as the reference; the control flow is arranged around ONE evaluation site (the
+// initial point is the first trip of the loop) and the path point of the best iterate is
+// kept, so get_closest_position (predef_path.py:251-255) needs no further evaluation.
+// Every lane runs its own iteration count (typically 10-47).
 template <class V>
-__device__ __forceinline__ double closest_u(PathCursor<V> &pc, double px, double py, int &nfev)
+__device__ __forceinline__ double closest_u(PathCursor<V> &pc, double px, double py, int &nfev, double &bx, double &by)
 {
-    const V &v = pc.v;
-    const double xatol = 1e-6;
+    const double xatol_3 = 1e-6 / 3.0;
     const int maxfun = 500;
     const double sqrt_eps = 1.4832396974191326e-08;      // sqrt(2.2e-16)
     const double golden_mean = 0.3819660112501051;        // 0.5*(3 - sqrt(5))
-    double a = -10.0, b = S::add(v.us(v.n_wps() - 1), 10.0);
+    double a = -10.0, b = S::add(pc.v.us(pc.N - 1), 10.0);
     double fulc = S::add(a, S::mul(golden_mean, S::sub(b, a)));
     double nfc = fulc, xf = fulc;
     double rat = 0.0, e = 0.0;
     double x = xf;
-    double fx = pc.dist(x, px, py);
-    int num = 1;
-    double fu;
-    double ffulc = fx, fnfc = fx;
-    double xm = S::mul(0.5, S::add(a, b));
-    double tol1 = S::add(S::mul(sqrt_eps, fabs(xf)), xatol / 3.0);
-    double tol2 = S::mul(2.0, tol1);
+    double fx = 0.0, ffulc = 0.0, fnfc = 0.0;
+    int num = 0;
+    bx = 0.0; by = 0.0;
+#pragma unroll 1
+    for (;;) {
+        // objective: np.linalg.norm(path(x) - pos) = sqrt(fma(dy, dy, dx*dx))  (BLAS ddot, predef_path.py:246)
+        double ex, ey;
+        pc.eval(x, ex, ey);
+        const double dx = S::sub(ex, px), dy = S::sub(ey, py);
+        const double fu = S::sqrt(S::fma(dy, dy, S::mul(dx, dx)));
+        if (num == 0) {
+            fx = fu; ffulc = fu; fnfc = fu; bx = ex; by = ey;
+        } else if (fu <= fx) {
+            if (x >= xf) a = xf; else b = xf;
+            fulc = nfc; ffulc = fnfc;
+            nfc = xf; fnfc = fx;
+            xf = x; fx = fu; bx = ex; by = ey;
+        } else {
+            if (x < xf) a = x; else b = x;
+            if ((fu <= fnfc) || (nfc == xf)) {
+                fulc = nfc; ffulc = fnfc;
+                nfc = x; fnfc = fu;
+            } else if ((fu <= ffulc) || (fulc == xf) || (fulc == nfc)) {
+                fulc = x; ffulc = fu;
+            }
+        }
+        num += 1;
+        const double xm = S::mul(0.5, S::add(a, b));
+        const double tol1 = S::add(S::mul(sqrt_eps, fabs(xf)), xatol_3);
+        const double tol2 = S::mul(2.0, tol1);
+        if (num > 1 && num >= maxfun) break;
+        if (!(fabs(S::sub(xf, xm)) > S::sub(tol2, S::mul(0.5, S::sub(b, a))))) break;
 
-    while (fabs(S::sub(xf, xm)) > S::sub(tol2, S::mul(0.5, S::sub(b, a)))) {
         bool golden = true;
-        if (fabs(e) > tol1) {
-            golden = false;
+        if (fabs(e) > tol1) {                              // try a parabolic step
             double r = S::mul(S::sub(xf, nfc), S::sub(fx, ffulc));
             double q = S::mul(S::sub(xf, fulc), S::sub(fx, fnfc));
             double p = S::sub(S::mul(S::sub(xf, fulc), q), S::mul(S::sub(xf, nfc), r));
@@ -371,44 +405,22 @@ __device__ __forceinline__ double closest_u(PathCursor<V> &pc, double px, double
             e = rat;
             if ((fabs(p) < fabs(S::mul(S::mul(0.5, q), r))) && (p > S::mul(q, S::sub(a, xf))) &&
                 (p < S::mul(q, S::sub(b, xf)))) {
+                golden = false;
                 rat = S::div(S::add(p, 0.0), q);
                 x = S::add(xf, rat);
                 if ((S::sub(x, a) < tol2) || (S::sub(b, x) < tol2)) {
-                    const double d = S::sub(xm, xf);
-                    const double si = (double)((d > 0.0) - (d < 0.0)) + (d == 0.0 ? 1.0 : 0.0);
-                    rat = S::mul(tol1, si);
+                    // si = sign(xm - xf) + ((xm - xf) == 0)
+                    rat = (S::sub(xm, xf) < 0.0) ? -tol1 : tol1;
                 }
-            } else {
-                golden = true;
             }
         }
         if (golden) {
             e = (xf >= xm) ? S::sub(a, xf) : S::sub(b, xf);
             rat = S::mul(golden_mean, e);
         }
-        const double si = (double)((rat > 0.0) - (rat < 0.0)) + (rat == 0.0 ? 1.0 : 0.0);
-        x = S::add(xf, S::mul(si, fmax(fabs(rat), tol1)));
-        fu = pc.dist(x, px, py);
-        num += 1;
-
-        if (fu <= fx) {
-            if (x >= xf) a = xf; else b = xf;
-            fulc = nfc; ffulc = fnfc;
-            nfc = xf; fnfc = fx;
-            xf = x; fx = fu;
-        } else {
-            if (x < xf) a = x; else b = x;
-            if ((fu <= fnfc) || (nfc == xf)) {
-                fulc = nfc; ffulc = fnfc;
-                nfc = x; fnfc = fu;
-            } else if ((fu <= ffulc) || (fulc == xf) || (fulc == nfc)) {
-                fulc = x; ffulc = fu;
-            }
-        }
-        xm = S::mul(0.5, S::add(a, b));
-        tol1 = S::add(S::mul(sqrt_eps, fabs(xf)), xatol / 3.0);
-        tol2 = S::mul(2.0, tol1);
-        if (num >= maxfun) break;
+        // x = xf + (sign(rat) + (rat == 0)) * max(|rat|, tol1)
+        const double mag = fmax(fabs(rat), tol1);
+        x = S::add(xf, (rat < 0.0) ? -mag : mag);
     }
     nfev = num;
     return xf;
@@ -677,7 +689,7 @@ struct ObsAux {
 
 template <class V, class Put>
 __device__ __forceinline__ void observe(const V &v, const D2dConst &c, EnvState &s, double rc0, double rs0,
-                                        const Nearest &nr, Put put, ObsAux &ax)
+                                        const Nearest &nr, Put put, ObsAux &ax, double2 *coef)
 {
     const double W = c.W, H = c.H;
     const double x = s.px[0], y = s.py[0], alpha = s.an[0];
@@ -718,10 +730,9 @@ __device__ __forceinline__ void observe(const V &v, const D2dConst &c, EnvState 
     // env:730-734.  The reference runs the identical fminbound a second time at
     // env:737; same arguments -> same result, evaluated once.
     int nfev;
-    PathCursor<V> pc(v);
-    const double u = closest_u(pc, x, y, nfev);
+    PathCursor<V> pc(v, coef);
     double cx, cy;
-    pc.eval(u, cx, cy);
+    const double u = closest_u(pc, x, y, nfev, cx, cy);
     ax.o19 = m1to1(cx, 0.0, W); ax.o20 = m1to1(cy, 0.0, H);
     put(19, ax.o19); put(20, ax.o20);
     ax.u_star = u; ax.nfev = nfev;

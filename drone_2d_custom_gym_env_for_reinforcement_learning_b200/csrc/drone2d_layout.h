@@ -41,6 +41,14 @@
 
 #include "../../include/drone2d.h"
 
+// Launch geometry of every per-env kernel (one lane per environment).
+#ifndef D2D_BLOCK
+#define D2D_BLOCK 128
+#endif
+#ifndef D2D_MIN_BLOCKS
+#define D2D_MIN_BLOCKS 4
+#endif
+
 #if defined(__CUDACC__)
 #define D2D_HD __host__ __device__
 #else
@@ -149,6 +157,7 @@ struct D2dParams {
     uint8_t *done;
     const uint8_t *mask;
     double *obs64, *info, *stats;
+    unsigned long long *role_cycles;   // [8] max clock64 span per role/phase of the last launches (profiling hook)
     uint64_t step_index;       // global step counter (keys the random-action stream)
     int auto_reset;
     D2dConst c;

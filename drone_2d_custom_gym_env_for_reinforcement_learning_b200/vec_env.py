@@ -352,6 +352,14 @@ class Drone2dVecEnv:
         _lib.check(self._L.d2d_episode_stats(self._h, self._dp(out), 1 if reset else 0))
         return dict(zip(STATS_KEYS, out.tolist()))
 
+    def role_cycles(self, reset=True):
+        """Profiling hook (d2d_debug_role_cycles): longest per-warp clock span per role / phase."""
+        out = (C.c_uint64 * 24)()
+        _lib.check(self._L.d2d_debug_role_cycles(self._h, out, 1 if reset else 0))
+        names = ("main_total", "refill_sample", "refill_observe", "physics", "obstacle_pass", "observe", "reward_swap")
+        return {nm: {"max": int(out[r]), "mean": int(out[8 + r]) // max(int(out[16 + r]), 1), "warps": int(out[16 + r])}
+                for r, nm in enumerate(names)}
+
     @property
     def launch_count(self):
         return int(self._L.d2d_launch_count(self._h))

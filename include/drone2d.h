@@ -161,6 +161,13 @@ int d2d_episode_stats_dev(d2d_env *env, double **stats_dev);
  * Env i uses its own path tables. */
 int d2d_debug_closest_u(d2d_env *env, const double *pos_dev, double *u_dev, int32_t *nfev_dev, void *stream);
 
+/* Profiling hook: per-warp clock64() spans since the last reset, for role/phase r =
+ * [0] a main lane's whole step, [1] the episode-sampling refill role, [2] the first-observation
+ * refill role, [3] thrust + rigid-body solve, [4] obstacle pass, [5] observation incl. the
+ * closest-point search, [6] reward / termination / swap; [7] unused.
+ * HOST uint64 [24], sync: out[r] = max, out[8 + r] = sum, out[16 + r] = number of warps. */
+int d2d_debug_role_cycles(d2d_env *env, uint64_t *out24, int reset_after);
+
 /* Number of kernels this library has launched on this handle. */
 int64_t d2d_launch_count(const d2d_env *env);
 

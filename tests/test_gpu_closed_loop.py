@@ -1,0 +1,49 @@
+"""Closed loop on the GPU: the shipped agent_19 actor (torch, on device) drives the batched
+environment; outcomes must reproduce the reference's evaluation artefacts and agree with the
+CPU oracle's closed loop (BASELINE config 4 and SURVEY Appendix B.3)."""
+import importlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+from test_closed_loop_cpu import FIX, check_against_fixture
+
+pytestmark = pytest.mark.gpu
+PKG = "drone_2d_custom_gym_env_for_reinforcement_learning_b200"
+SETTINGS = [("test", s) for s in ("corridor", "S_corridor", "parallel", "S_parallel", "perpendicular", "large", "impossible")] + \
+           [("curriculum", "stage_%d" % k) for k in range(1, 6)]
+
+
+@pytest.mark.parametrize("mode,scenario", SETTINGS)
+def test_agent19_outcomes_match_reference_fixtures(mode, scenario):
+    import torch
+    pkg = importlib.import_module(PKG)
+    policy = importlib.import_module(PKG + ".policy")
+    n = 4096
+    env = pkg.Drone2dVecEnv(n, seed=5, mode=mode, scenario=scenario)
+    actor = policy.MlpActor.load(os.path.join(GOLDEN, "agent_19_policy.npz"), env.device)
+    res = policy.rollout_one_episode_each(env, actor, seed=1)
+    env.close()
+    assert res["finished"].all()          # n_steps = 1100 ends every episode
+    check_against_fixture(res, FIX[scenario], n, scenario)
+
+
+def test_gpu_and_oracle_closed_loops_agree():
+    """Same spec, two implementations, independent random streams: rates agree within sampling noise."""
+    from oracle import closed_loop
+    pkg = importlib.import_module(PKG)
+    policy = importlib.import_module(PKG + ".policy")
+    n_gpu, n_cpu = 8192, 400
+    env = pkg.Drone2dVecEnv(n_gpu, seed=9, mode="test", scenario="corridor")
+    actor = policy.MlpActor.load(os.path.join(GOLDEN, "agent_19_policy.npz"), env.device)
+    g = policy.rollout_one_episode_each(env, actor, seed=2)
+    env.close()
+    c = closed_loop.evaluate("test", "corridor", n_cpu, seed=4)
+    for key in ("n_successful_runs", "n_collisions"):
+        pg, pc = g[key].mean(), c[key].mean()
+        sigma = np.sqrt(max(pc * (1 - pc), 0.02) / n_cpu + max(pg * (1 - pg), 0.02) / n_gpu)
+        assert abs(pg - pc) <= 4 * sigma, (key, pg, pc, sigma)
+    assert abs(g["env_steps"].mean() - c["env_steps"].mean()) <= 0.08 * c["env_steps"].mean()

@@ -34,11 +34,17 @@ def timed(n, k0):
 
 for k in range(3):
     env.step_device(ring[k], terminal_obs=False)
+env.role_cycles()
 early = timed(10, 3)
+rc_early = env.role_cycles()
 for k in range(400):
     env.step_device(ring[k % 16], terminal_obs=False)
+env.role_cycles()
 steady = timed(400, 0)
+rc_steady = env.role_cycles()
 st = env.episode_stats()
 print(json.dumps({"lib": os.path.basename(os.environ.get("D2D_LIB", "default")), "envs": E, "scenario": scen,
                   "early_us": round(early, 1), "steady_us": round(steady, 1),
-                  "steady_Msteps_s": round(E / steady, 1), "mean_ep_len": round(st["env_steps"] / max(st["episodes"], 1), 1)}))
+                  "steady_Msteps_s": round(E / steady, 1), "mean_ep_len": round(st["env_steps"] / max(st["episodes"], 1), 1),
+                  "kcyc_early(max,mean)": {k: (v["max"] // 1000, v["mean"] // 1000) for k, v in rc_early.items()},
+                  "kcyc_steady(max,mean)": {k: (v["max"] // 1000, v["mean"] // 1000) for k, v in rc_steady.items()}}))
