@@ -1,0 +1,181 @@
+"""GPU-only: (1) the closest-point search is bit-exact against the oracle on identical
+inputs, (2) the fused re-spawn reproduces the oracle's restatement of the reference reset on
+the same counter-based stream, (3) state/tables round-trip through the ABI, (4) sharding does
+not change an environment's episodes."""
+import importlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from oracle import ref_port
+from oracle.philox_reset import PhiloxDraws
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+PKG = "drone_2d_custom_gym_env_for_reinforcement_learning_b200"
+
+
+@pytest.fixture(scope="module")
+def pkg():
+    return importlib.import_module(PKG)
+
+
+@pytest.mark.parametrize("scenario", ["corridor", "S_corridor", "S_parallel", "large", "impossible"])
+def test_closest_u_bit_exact_shared_tables(pkg, scenario):
+    """QPMI2D.get_closest_u (predef_path.py:226-248): identical positions in -> identical u* and
+    identical number of Brent evaluations out (float64 bit patterns compared)."""
+    n = 4096
+    env = pkg.Drone2dVecEnv(n, seed=1, mode="test", scenario=scenario)
+    env.reset_device()
+    rng = np.random.RandomState(3)
+    pos = np.stack([rng.uniform(-100, 1400, n), rng.uniform(-100, 1400, n)], 1)
+    u_gpu, nfev_gpu = env.closest_u(pos)
+    path, _ = oracle.load_scenario(scenario)
+    for i in range(n):
+        u, nfev, _ = oracle.closest_u(path, pos[i, 0], pos[i, 1])
+        assert nfev == nfev_gpu[i], (i, pos[i], u, u_gpu[i])
+        assert u == u_gpu[i], (i, pos[i], u, u_gpu[i])
+    env.close()
+
+
+def test_closest_u_matches_reference_golden_vectors(pkg):
+    """Directly against scipy.fminbound outputs recorded from the reference's own predef_path.py."""
+    kats = json.load(open(os.path.join(GOLDEN, "path_kats.json")))
+    total = exact = 0
+    for scenario in ("corridor", "S_corridor", "S_parallel", "large", "impossible", "parallel", "perpendicular"):
+        rec = kats[scenario]
+        n = len(rec["closest"])
+        env = pkg.Drone2dVecEnv(n, seed=1, mode="test", scenario=scenario)
+        env.reset_device()
+        u_gpu, nfev_gpu = env.closest_u(np.array([c["pos"] for c in rec["closest"]]))
+        for k, c in enumerate(rec["closest"]):
+            assert nfev_gpu[k] == c["nfev"]
+            assert abs(u_gpu[k] - c["u"]) <= 1e-9
+            exact += (u_gpu[k] == c["u"])
+            total += 1
+        env.close()
+    assert exact >= total - 1          # 1 of the 296 golden cases differs in the last bits (see oracle tests)
+
+
+def test_closest_u_bit_exact_per_env_tables(pkg):
+    n = 1024
+    env = pkg.Drone2dVecEnv(n, seed=4, mode="curriculum", scenario="stage_1")
+    env.reset_device()
+    tb = env.get_tables()
+    rng = np.random.RandomState(5)
+    pos = np.stack([rng.uniform(0, 1300, n), rng.uniform(0, 1300, n)], 1)
+    u_gpu, nfev_gpu = env.closest_u(pos)
+    for i in range(n):
+        path = oracle.make_path(tb["wps"][i, :12], tb["us"][i, :12], tb["xparams"][i, :10], tb["yparams"][i, :10])
+        u, nfev, _ = oracle.closest_u(path, pos[i, 0], pos[i, 1])
+        assert (u, nfev) == (u_gpu[i], nfev_gpu[i]), i
+    env.close()
+
+
+def _oracle_episode(mode, scenario, seed, env_id, episode, kwargs=None):
+    draws = PhiloxDraws(seed, env_id, episode)
+    return ref_port.reset_tables(mode, scenario, kwargs or {}, draws)
+
+
+@pytest.mark.parametrize("stage", [1, 2, 3, 4, 5])
+def test_fused_reset_matches_oracle_reset_on_the_same_stream(pkg, stage):
+    """a15-a18: waypoints, chord parameters, path polynomials, obstacle sampler, spawn pose."""
+    n, seed, base = 192, 1234 + stage, 1000
+    scen = "stage_%d" % stage
+    env = pkg.Drone2dVecEnv(n, seed=seed, env_id_base=base, mode="curriculum", scenario=scen)
+    env.reset_device()
+    tb, st = env.get_tables(), env.get_state()
+    for i in range(n):
+        path, obstacles, (x, y, a) = _oracle_episode("curriculum", scen, seed, base + i, 0)
+        np.testing.assert_allclose(tb["wps"][i, :12], path.waypoints, rtol=0, atol=1e-9)
+        np.testing.assert_allclose(tb["us"][i, :12], path.us, rtol=0, atol=1e-9)
+        # the kernel solves the 3-point quadratics in Newton form, the reference inverts a
+        # Vandermonde matrix: compare the polynomials where they are used, not their coefficients
+        gp = oracle.make_path(tb["wps"][i, :12], tb["us"][i, :12], tb["xparams"][i, :10], tb["yparams"][i, :10])
+        op = path.to_struct()
+        for u in np.linspace(-10, path.length + 10, 23):
+            np.testing.assert_allclose(oracle.path_eval(gp, u), oracle.path_eval(op, u), rtol=0, atol=2e-8)
+        assert tb["n_obs"][i] == len(obstacles), (i, tb["n_obs"][i], len(obstacles))
+        if obstacles:
+            np.testing.assert_allclose(tb["obstacles"][i, :len(obstacles)], np.array(obstacles), rtol=0, atol=1e-7)
+        np.testing.assert_allclose(st[i, [0, 1, 4]], [x, y, a], rtol=0, atol=1e-9)
+        assert st[i, 35] == 0 and st[i, 32] == 0
+    env.close()
+
+
+def test_auto_reset_episodes_follow_the_stream(pkg):
+    """Episodes k = 1, 2, ... reached through the prefetch / swap path equal the oracle's episode k."""
+    import torch
+    n, seed = 256, 77
+    env = pkg.Drone2dVecEnv(n, seed=seed, mode="curriculum", scenario="stage_5")
+    env.reset_device()
+    for _ in range(260):
+        env.step_device(None)                # in-kernel random actions
+    tb, st = env.get_tables(), env.get_state()
+    episodes = st[:, 35].astype(int)
+    assert episodes.max() >= 2
+    checked = 0
+    for i in np.argsort(-episodes)[:64]:
+        path, obstacles, _ = _oracle_episode("curriculum", "stage_5", seed, i, int(episodes[i]))
+        np.testing.assert_allclose(tb["wps"][i, :12], path.waypoints, rtol=0, atol=1e-9)
+        assert tb["n_obs"][i] == len(obstacles)
+        if obstacles:
+            np.testing.assert_allclose(tb["obstacles"][i, :len(obstacles)], np.array(obstacles), rtol=0, atol=1e-7)
+        checked += 1
+    assert checked == 64
+    stats = env.episode_stats()
+    assert stats["episodes"] == episodes.sum()
+    env.close()
+
+
+def test_test_mode_spawn_matches_oracle_stream(pkg):
+    n, seed = 512, 5
+    env = pkg.Drone2dVecEnv(n, seed=seed, mode="test", scenario="S_corridor")
+    env.reset_device()
+    st = env.get_state()
+    for i in range(n):
+        _, _, (x, y, a) = _oracle_episode("test", "S_corridor", seed, i, 0)
+        np.testing.assert_allclose(st[i, [0, 1, 4]], [x, y, a], rtol=0, atol=1e-9)
+    assert st[:, 0].min() >= 50 and st[:, 0].max() <= 200 and st[:, 1].min() >= 150 and st[:, 1].max() <= 1000
+    env.close()
+
+
+def test_sharding_does_not_change_episodes(pkg):
+    """Envs are keyed by GLOBAL id: one 512-env handle == two 256-env handles with env_id_base 0 / 256."""
+    full = pkg.Drone2dVecEnv(512, seed=3, mode="curriculum", scenario="stage_5")
+    lo = pkg.Drone2dVecEnv(256, seed=3, env_id_base=0, mode="curriculum", scenario="stage_5")
+    hi = pkg.Drone2dVecEnv(256, seed=3, env_id_base=256, mode="curriculum", scenario="stage_5")
+    for e in (full, lo, hi):
+        e.reset_device()
+    for _ in range(120):
+        for e in (full, lo, hi):
+            e.step_device(None)
+    a = full.get_state()
+    b = np.concatenate([lo.get_state(), hi.get_state()])
+    assert np.array_equal(a, b)
+    sa, sl, sh = full.episode_stats(), lo.episode_stats(), hi.episode_stats()
+    assert sa["episodes"] == sl["episodes"] + sh["episodes"] > 0
+    assert abs(sa["total_reward"] - (sl["total_reward"] + sh["total_reward"])) <= 1e-6 * abs(sa["total_reward"])
+    for e in (full, lo, hi):
+        e.close()
+
+
+def test_state_and_table_round_trip(pkg):
+    env = pkg.Drone2dVecEnv(64, seed=8, mode="curriculum", scenario="stage_5")
+    env.reset_device()
+    st, tb = env.get_state(), env.get_tables()
+    st2 = st.copy()
+    st2[:, 0] += 3.0
+    st2[:, 35] = 5
+    env.set_state(st2)
+    assert np.array_equal(env.get_state(), st2)
+    tb2 = {k: v.copy() for k, v in tb.items()}
+    tb2["obstacles"][:, 0, 2] += 1.0
+    env.set_tables(tb2["wps"], tb2["us"], tb2["xparams"], tb2["yparams"], tb2["n_obs"], tb2["obstacles"])
+    got = env.get_tables()
+    for k in tb2:
+        assert np.array_equal(got[k], tb2[k]), k
+    env.close()
