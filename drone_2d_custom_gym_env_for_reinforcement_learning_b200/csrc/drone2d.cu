@@ -81,12 +81,12 @@ __device__ __noinline__ int first_observation(const D2dParams &p, const D2dShare
 //   stage A  sample the episode: tables + spawn pose            (stg_meta = {-1, n_obs, 0, target})
 //   stage B  first observation of the staged episode, publish   (stg_meta = {target, n_obs, latch, target})
 template <bool PER_ENV>
-__device__ __forceinline__ void stage_sample(const D2dParams &p, int64_t e)
+__device__ __forceinline__ void stage_sample(const D2dParams &p, int64_t e, double *us_s)
 {
     const int4 m = p.meta[e];
     const int target = m.z + 1;
     const int par = (m.y & D2D_F_PARITY) ? 0 : 1;
-    const ResetOut ro = reset_env<PER_ENV>(p, e, target, par);
+    const ResetOut ro = reset_env<PER_ENV>(p, e, target, par, us_s);
     p.stg_xy[e] = make_double2(ro.x, ro.y);
     p.stg_an[e] = make_double2(ro.angle, 0.0);
     p.stg_meta[e] = make_int4(-1, ro.n_obs, par, target);
@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(D2D_BLOCK, D2D_MIN_BLOCKS) d2d_step_kernel(con
             const int cnt = qa_cnt[q_read];
             for (int t = first; t < cnt; t += total) {
                 const int e = qa[(int64_t)q_read * p.np + t];
-                stage_sample<PER_ENV>(p, e);
+                stage_sample<PER_ENV>(p, e, &s_us[PER_ENV ? tid : 0]);
                 const int slot = atomicAdd(&qb_cnt[q_write], 1);
                 qb[(int64_t)q_write * p.np + slot] = e;
                 qb_tgt[(int64_t)q_write * p.np + slot] = p.stg_meta[e].w;
@@ -272,7 +272,7 @@ __global__ void __launch_bounds__(D2D_BLOCK, D2D_MIN_BLOCKS) d2d_step_kernel(con
                 } else {
                     // slot not ready (episode ended one step after the previous one, or state was
                     // injected): sample in the lane, into the live table buffer
-                    const ResetOut ro = reset_env<PER_ENV>(p, i, next_ep, par);
+                    const ResetOut ro = reset_env<PER_ENV>(p, i, next_ep, par, &s_us[PER_ENV ? tid : 0]);
                     nx = ro.x; ny = ro.y; na = ro.angle; n_obs = ro.n_obs;
                     new_flags = D2D_F_INIT | (par ? D2D_F_PARITY : 0);
                     new_flags |= first_observation<PER_ENV>(p, &s_tab, i, nx, ny, na, n_obs, par, row, nullptr, nullptr,
@@ -323,6 +323,7 @@ __global__ void __launch_bounds__(D2D_BLOCK) d2d_reset_kernel(const __grid_const
 {
     __shared__ D2dSharedTables s_tab;
     __shared__ double2 s_coef[6 * D2D_BLOCK];
+    __shared__ double s_us[PER_ENV ? D2D_MAX_WPS * D2D_BLOCK : 1];
     const int tid = threadIdx.x;
     const int64_t i = (int64_t)blockIdx.x * D2D_BLOCK + tid;
     if (!PER_ENV) stage_shared_tables(p, &s_tab, tid, D2D_BLOCK);
@@ -333,7 +334,7 @@ __global__ void __launch_bounds__(D2D_BLOCK) d2d_reset_kernel(const __grid_const
     const int4 m = p.meta[i];
     const int episode = (m.y & D2D_F_INIT) ? m.z + 1 : 0;
     const int par = (m.y & D2D_F_PARITY) ? 1 : 0;
-    const ResetOut ro = reset_env<PER_ENV>(p, i, episode, par);
+    const ResetOut ro = reset_env<PER_ENV>(p, i, episode, par, &s_us[PER_ENV ? tid : 0]);
     const int latch = first_observation<PER_ENV>(p, &s_tab, i, ro.x, ro.y, ro.angle, ro.n_obs, par,
                                                  p.obs ? p.obs + i * D2D_OBS_DIM : nullptr,
                                                  p.obs64 ? p.obs64 + i * D2D_OBS_DIM : nullptr,
@@ -343,7 +344,7 @@ __global__ void __launch_bounds__(D2D_BLOCK) d2d_reset_kernel(const __grid_const
     s.flags = D2D_F_INIT | (par ? D2D_F_PARITY : 0) | latch;
     s.episode = episode; s.n_obs = ro.n_obs;
     store_state(p, i, s);
-    stage_sample<PER_ENV>(p, i);
+    stage_sample<PER_ENV>(p, i, &s_us[PER_ENV ? tid : 0]);
     stage_observe<PER_ENV>(p, &s_tab, i, episode + 1, &s_coef[tid]);
 }
 
@@ -783,6 +784,13 @@ int d2d_step(d2d_env *e, const float *actions_dev, float *obs_dev, float *reward
     return D2D_OK;
 }
 
+static bool is_pinned_host(const void *ptr)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, ptr) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
 int d2d_step_host(d2d_env *e, const float *actions_host, float *obs_host, float *reward_host, uint8_t *done_host,
                   int auto_reset, void *stream)
 {
@@ -798,19 +806,26 @@ int d2d_step_host(d2d_env *e, const float *actions_host, float *obs_host, float 
         CUDA_TRY(cudaHostAlloc(&e->h_rew, b_rew, cudaHostAllocDefault)); CUDA_TRY(cudaHostAlloc(&e->h_done, n, cudaHostAllocDefault));
     }
     cudaStream_t st = (cudaStream_t)stream;
+    // Page-locked caller buffers (cudaHostAlloc / cudaHostRegister / torch pin_memory) are used
+    // directly; pageable ones go through the handle's pinned staging buffers.
+    const bool pin_a = actions_host && is_pinned_host(actions_host);
+    const bool pin_o = is_pinned_host(obs_host), pin_r = is_pinned_host(reward_host), pin_d = is_pinned_host(done_host);
     const float *dact = nullptr;
     if (actions_host) {
-        memcpy(e->h_act, actions_host, b_act);
-        CUDA_TRY(cudaMemcpyAsync(e->d_act, e->h_act, b_act, cudaMemcpyHostToDevice, st));
+        const float *src = actions_host;
+        if (!pin_a) { memcpy(e->h_act, actions_host, b_act); src = e->h_act; }
+        CUDA_TRY(cudaMemcpyAsync(e->d_act, src, b_act, cudaMemcpyHostToDevice, st));
         dact = e->d_act;
     }
     int rc = d2d_step(e, dact, e->d_obs, e->d_rew, e->d_done, nullptr, auto_reset, stream);
     if (rc) return rc;
-    CUDA_TRY(cudaMemcpyAsync(e->h_obs, e->d_obs, b_obs, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaMemcpyAsync(e->h_rew, e->d_rew, b_rew, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaMemcpyAsync(e->h_done, e->d_done, n, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(pin_o ? obs_host : e->h_obs, e->d_obs, b_obs, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(pin_r ? reward_host : e->h_rew, e->d_rew, b_rew, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(pin_d ? done_host : e->h_done, e->d_done, n, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
-    memcpy(obs_host, e->h_obs, b_obs); memcpy(reward_host, e->h_rew, b_rew); memcpy(done_host, e->h_done, n);
+    if (!pin_o) memcpy(obs_host, e->h_obs, b_obs);
+    if (!pin_r) memcpy(reward_host, e->h_rew, b_rew);
+    if (!pin_d) memcpy(done_host, e->h_done, n);
     return D2D_OK;
 }
 

@@ -277,11 +277,13 @@ struct PathCursor {
     // column (coef[r * D2D_BLOCK], r = 0..5 = a1, b1, c1, a2, b2, c2): 24 registers fewer
     // during the search, 6 conflict-free LDS.128 per evaluation instead.
     double2 *coef;
+    double inv_seg;      // (N-1)/L: initial guess of the segment index (any guess is corrected exactly)
 
     __device__ __forceinline__ PathCursor(const V &v_, double2 *coef_) : v(v_), N(v_.n_wps()), blend(false), coef(coef_)
     {
         us0 = v.us(0); us1 = v.us(1);
         last_start = S::sub(v.us(N - 2), 0.001);
+        inv_seg = (double)(N - 1) / v.us(N - 1);
         vlo_x = vlo_i = CUDART_INF; vhi_i = vhi_x = -CUDART_INF;       // empty interval: first use locates
         lo = un1 = len = rlen = 0.0;
     }
@@ -302,7 +304,11 @@ struct PathCursor {
             blend = false; vlo_i = last_start;
             coef[3 * D2D_BLOCK] = v.pa(rows - 1); coef[4 * D2D_BLOCK] = v.pb(rows - 1); coef[5 * D2D_BLOCK] = v.pc(rows - 1);
         } else {
-            const int n = u_index(v, u, N);
+            // get_u_index (predef_path.py:53-63) = number of us[k], k >= 1, below u: start from the
+            // uniform-spacing guess and walk to the exact answer (0-1 steps on the reference's paths)
+            int n = min(max((int)(u * inv_seg), 0), N - 2);
+            while (n < N - 1 && u > v.us(n + 1)) n++;
+            while (n > 0 && !(u > v.us(n))) n--;
             blend = true;
             lo = v.us(n); un1 = v.us(n + 1);
             if (n == 0) { vhi_x = us0; }                             // u < us[0]: rows -1 (= last) and 0
@@ -642,34 +648,45 @@ __device__ __forceinline__ bool scan_obstacles(const V &v, const D2dConst &c, do
     // corners of the unrotated box: (+-hw + x, +-hh + y)   (v1 + body.position, env:955)
     const double cxp = S::add(c.hw, x), cxm = S::add(-c.hw, x);
     const double cyp = S::add(c.hh, y), cym = S::add(-c.hh, y);
-    for (int k = 0; k < n; k++) {
-        double ox, oy, orad;
-        v.obstacle(k, ox, oy, orad);
-        if (test_collision) {
-            const double dx = ox - x, dy = oy - y;
-            const double qx = rc0 * dx + rs0 * dy, qy = rc0 * dy - rs0 * dx;
-            const double ex = fmax(fabs(qx) - c.hw, 0.0), ey = fmax(fabs(qy) - c.hh, 0.0);
-            hit = hit || (sqrt(ex * ex + ey * ey) <= orad);
+    for (int k0 = 0; k0 < n; k0 += 4) {
+        // batches of 4: the per-lane table loads of a batch are issued back to back
+        double bx[4], by[4], br[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            bx[j] = 0.0; by[j] = 0.0; br[j] = 0.0;
+            if (k0 + j < n) v.obstacle(k0 + j, bx[j], by[j], br[j]);
         }
-        // min over corners of sqrt(dx^2+dy^2) - r: the rounded operations are monotone,
-        // so the minimum separates per axis and one sqrt suffices (bit-identical).
-        const double dxp = S::sub(cxp, ox), dxm = S::sub(cxm, ox);
-        const double dyp = S::sub(cyp, oy), dym = S::sub(cym, oy);
-        const double qx2 = fmin(S::mul(dxp, dxp), S::mul(dxm, dxm));
-        const double qy2 = fmin(S::mul(dyp, dyp), S::mul(dym, dym));
-        const double dist = S::sub(S::sqrt(S::add(qx2, qy2)), orad);
-        // stable insertion (strict <: ties keep the lower index first, like sorted())
-        if (dist < nr.d[2]) {
-            if (dist < nr.d[1]) {
-                nr.d[2] = nr.d[1]; nr.idx[2] = nr.idx[1]; nr.ox[2] = nr.ox[1]; nr.oy[2] = nr.oy[1];
-                if (dist < nr.d[0]) {
-                    nr.d[1] = nr.d[0]; nr.idx[1] = nr.idx[0]; nr.ox[1] = nr.ox[0]; nr.oy[1] = nr.oy[0];
-                    nr.d[0] = dist; nr.idx[0] = k; nr.ox[0] = ox; nr.oy[0] = oy;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int k = k0 + j;
+            if (k >= n) break;
+            const double ox = bx[j], oy = by[j], orad = br[j];
+            if (test_collision) {
+                const double dx = ox - x, dy = oy - y;
+                const double qx = rc0 * dx + rs0 * dy, qy = rc0 * dy - rs0 * dx;
+                const double ex = fmax(fabs(qx) - c.hw, 0.0), ey = fmax(fabs(qy) - c.hh, 0.0);
+                hit = hit || (sqrt(ex * ex + ey * ey) <= orad);
+            }
+            // min over corners of sqrt(dx^2+dy^2) - r: the rounded operations are monotone,
+            // so the minimum separates per axis and one sqrt suffices (bit-identical).
+            const double dxp = S::sub(cxp, ox), dxm = S::sub(cxm, ox);
+            const double dyp = S::sub(cyp, oy), dym = S::sub(cym, oy);
+            const double qx2 = fmin(S::mul(dxp, dxp), S::mul(dxm, dxm));
+            const double qy2 = fmin(S::mul(dyp, dyp), S::mul(dym, dym));
+            const double dist = S::sub(S::sqrt(S::add(qx2, qy2)), orad);
+            // stable insertion (strict <: ties keep the lower index first, like sorted())
+            if (dist < nr.d[2]) {
+                if (dist < nr.d[1]) {
+                    nr.d[2] = nr.d[1]; nr.idx[2] = nr.idx[1]; nr.ox[2] = nr.ox[1]; nr.oy[2] = nr.oy[1];
+                    if (dist < nr.d[0]) {
+                        nr.d[1] = nr.d[0]; nr.idx[1] = nr.idx[0]; nr.ox[1] = nr.ox[0]; nr.oy[1] = nr.oy[0];
+                        nr.d[0] = dist; nr.idx[0] = k; nr.ox[0] = ox; nr.oy[0] = oy;
+                    } else {
+                        nr.d[1] = dist; nr.idx[1] = k; nr.ox[1] = ox; nr.oy[1] = oy;
+                    }
                 } else {
-                    nr.d[1] = dist; nr.idx[1] = k; nr.ox[1] = ox; nr.oy[1] = oy;
+                    nr.d[2] = dist; nr.idx[2] = k; nr.ox[2] = ox; nr.oy[2] = oy;
                 }
-            } else {
-                nr.d[2] = dist; nr.idx[2] = k; nr.ox[2] = ox; nr.oy[2] = oy;
             }
         }
     }
@@ -840,6 +857,51 @@ __device__ __forceinline__ void reward_and_done(const D2dConst &c, EnvState &s, 
 //   test:       x, y, spawn angle
 //   sampler attempt: u_obs, normal(mean,std) (2 draws), radius
 // ---------------------------------------------------------------------------
+// QPMI2D.__call__ and calculate_gradient (predef_path.py:88-188) at the same u with ONE segment
+// lookup (the obstacle sampler needs both, obstacles.py:65-69).  Note the two reference branches
+// differ: the point uses the last row from us[-2] - 0.001 on, the gradient from us[-2] on.
+template <class V>
+__device__ __forceinline__ void path_point_and_gradient(const V &v, double u, double &x, double &y, double &gx, double &gy)
+{
+    const int N = v.n_wps(), rows = N - 2;
+    const double us0 = v.us(0), us1 = v.us(1), usm2 = v.us(N - 2);
+    const double uu = S::mul(u, u);
+    const bool first = (u >= us0 && u <= us1);
+    const bool p_last = !first && (u >= S::sub(usm2, 0.001));
+    const bool g_last = !first && (u >= usm2);
+    if (first || (p_last && g_last)) {
+        const int r = first ? 0 : rows - 1;
+        const double2 a = v.pa(r), b = v.pb(r), c = v.pc(r);
+        x = poly2(a.x, b.x, c.x, u, uu); y = poly2(a.y, b.y, c.y, u, uu);
+        gx = S::add(S::mul(S::mul(a.x, u), 2.0), b.x); gy = S::add(S::mul(S::mul(a.y, u), 2.0), b.y);
+        return;
+    }
+    int n = min(max((int)(u * ((double)(N - 1) / v.us(N - 1))), 0), N - 2);
+    while (n < N - 1 && u > v.us(n + 1)) n++;
+    while (n > 0 && !(u > v.us(n))) n--;
+    const double un = v.us(n), un1 = v.us(n + 1);
+    const double len = S::sub(un1, un);
+    const double mu_r = S::div(S::sub(u, un), len), mu_f = S::div(S::sub(un1, u), len);
+    const int r1 = (n - 1 < 0) ? rows - 1 : n - 1;
+    const double2 a1 = v.pa(r1), b1 = v.pb(r1), c1 = v.pc(r1), a2 = v.pa(n), b2 = v.pb(n), c2 = v.pc(n);
+    if (p_last) {                      // u in [us[-2] - 0.001, us[-2]): point from the last row alone
+        const double2 a = v.pa(rows - 1), b = v.pb(rows - 1), c = v.pc(rows - 1);
+        x = poly2(a.x, b.x, c.x, u, uu); y = poly2(a.y, b.y, c.y, u, uu);
+    } else {
+        const double x1 = poly2(a1.x, b1.x, c1.x, u, uu), y1 = poly2(a1.y, b1.y, c1.y, u, uu);
+        const double x2 = poly2(a2.x, b2.x, c2.x, u, uu), y2 = poly2(a2.y, b2.y, c2.y, u, uu);
+        x = S::add(S::mul(mu_r, x2), S::mul(mu_f, x1));
+        y = S::add(S::mul(mu_r, y2), S::mul(mu_f, y1));
+    }
+    const double dx1 = S::add(S::mul(S::mul(a1.x, u), 2.0), b1.x), dy1 = S::add(S::mul(S::mul(a1.y, u), 2.0), b1.y);
+    const double dx2 = S::add(S::mul(S::mul(a2.x, u), 2.0), b2.x), dy2 = S::add(S::mul(S::mul(a2.y, u), 2.0), b2.y);
+    gx = S::add(S::mul(mu_r, dx2), S::mul(mu_f, dx1));
+    gy = S::add(S::mul(mu_r, dy2), S::mul(mu_f, dy1));
+}
+
+// generate_obstacles_around_path (obstacles.py:58-89): rejection sampler.  The offset direction
+// (cos, sin)(atan2(gy, gx) - pi/2) is (gy, -gx)/|g|, evaluated without the transcendental round trip
+// (differs from the reference's value by rounding only; reset parity tolerance 1e-7 px).
 __device__ __forceinline__ int sample_obstacles(const D2dParams &p, EnvView &ev, ResetRng &rng, int slot, int count,
                                                 double mean, double sd, bool on_path)
 {
@@ -848,21 +910,20 @@ __device__ __forceinline__ int sample_obstacles(const D2dParams &p, EnvView &ev,
     while (made < count && slot < D2D_MAX_OBS_ENV && attempts < 4096) {   // obstacles.py:63 `while num_obstacles < n`
         attempts++;
         const double u_obs = rng.uniform(0.20 * L, 0.90 * L);
-        double gx, gy, x, y;
-        path_gradient(ev, u_obs, gx, gy);
-        const double ang = atan2(gy, gx);
         const double dist = rng.normal(mean, sd);
-        path_eval(ev, u_obs, x, y);
-        double sn, cs;
-        sincos(ang - D2D_PI / 2, &sn, &cs);
-        const double ox = x + dist * cs, oy = y + dist * sn;
         const double size = rng.uniform(10.0, 50.0);
-        const double ddx = ox - x, ddy = oy - y;
+        double gx, gy, x, y;
+        path_point_and_gradient(ev, u_obs, x, y, gx, gy);
         if (on_path) {
             p.obxy[ev.orow(slot)] = make_double2(x, y);
             p.obr[ev.orow(slot)] = size;
             slot++; made++;
-        } else if (sqrt(ddx * ddx + ddy * ddy) > size + 10.0) {
+            continue;
+        }
+        const double inv_g = rsqrt(gx * gx + gy * gy);
+        const double ox = x + dist * (gy * inv_g), oy = y + dist * (-gx * inv_g);
+        const double ddx = ox - x, ddy = oy - y;
+        if (sqrt(ddx * ddx + ddy * ddy) > size + 10.0) {
             p.obxy[ev.orow(slot)] = make_double2(ox, oy);
             p.obr[ev.orow(slot)] = size;
             slot++; made++;
@@ -881,7 +942,7 @@ struct ResetOut {
 };
 
 template <bool PER_ENV>
-__device__ __noinline__ ResetOut reset_env(const D2dParams &p, int64_t i, int episode, int par)
+__device__ __noinline__ ResetOut reset_env(const D2dParams &p, int64_t i, int episode, int par, double *us_s)
 {
     const D2dConst &c = p.c;
     ResetRng rng((uint32_t)(c.env_id_base + i), (uint32_t)episode, c.seed_lo, c.seed_hi);
@@ -893,7 +954,7 @@ __device__ __noinline__ ResetOut reset_env(const D2dParams &p, int64_t i, int ep
         return ResetOut{x, y, a, 0};
     }
     // ---- curriculum: random path (predef_path.py:307-363) ----
-    EnvView ev{&p, i, 0, par};
+    EnvView ev{&p, i, 0, par, us_s};     // us[] of the new path is mirrored in the lane's shared-memory column
     const int N = c.n_wps;
     int corner = 2;                                              // 'DR' when random_path_spawn is False (env:214)
     if (c.random_path_spawn) corner = rng.randint(c.corner_lo, c.corner_hi);   // 1 DL, 2 DR, 3 UL, 4 UR (env:202-211)
@@ -913,6 +974,7 @@ __device__ __noinline__ ResetOut reset_env(const D2dParams &p, int64_t i, int ep
     double xa = 0.0, ya = 0.0, xb = wx, yb = wy;                  // waypoints k-2, k-1
     p.wps[ev.wrow(0)] = make_double2(wx, wy);
     p.us[ev.wrow(0)] = 0.0;
+    us_s[0] = 0.0;
     for (int k = 1; k < N; k++) {
         const double az = rng.uniform(az_lo, az_hi);
         double sn, cs;
@@ -922,6 +984,7 @@ __device__ __noinline__ ResetOut reset_env(const D2dParams &p, int64_t i, int ep
         u_cur = u_prev + sqrt(ddx * ddx + ddy * ddy);
         p.wps[ev.wrow(k)] = make_double2(nx, ny);
         p.us[ev.wrow(k)] = u_cur;
+        us_s[k * D2D_US_STRIDE] = u_cur;
         if (k >= 2) {
             const double u0 = u_prev2, u1 = u_prev, u2 = u_cur;
             const double dx01 = (xb - xa) / (u1 - u0), dx12 = (nx - xb) / (u2 - u1);
