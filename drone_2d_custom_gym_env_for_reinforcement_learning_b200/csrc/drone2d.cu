@@ -58,8 +58,8 @@ __device__ __noinline__ int first_observation(const D2dParams &p, const D2dShare
     EnvState s;
     s.px[0] = x; s.py[0] = y; s.an[0] = angle; s.vx[0] = 0.0; s.vy[0] = 0.0; s.om[0] = 0.0;
     s.flags = 0;
-    double rc0, rs0;
-    sincos(angle, &rs0, &rc0);
+    const double2 sc0 = sincos2(angle);
+    const double rs0 = sc0.x, rc0 = sc0.y;
     typename ViewOf<PER_ENV>::type v = ViewOf<PER_ENV>::make(p, tab, i, n_obs, par);
     Nearest nr;
     scan_obstacles(v, p.c, x, y, rc0, rs0, false, nr);

@@ -74,6 +74,33 @@ __device__ __forceinline__ double m1to1(double v, double lo, double hi) { return
 __device__ __forceinline__ double invm1to1(double v, double lo, double hi) { return (v + 1.0) * (hi - lo) / 2.0 + lo; }
 __device__ __forceinline__ double clipd(double v, double lo, double hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
+// Out-of-line transcendentals: CUDA's double sincos/atan2 expand to ~150 instructions each at
+// every call site; the step calls them ~20 times, which made the kernel's hot path several times
+// larger than the instruction cache.  One shared copy each (results returned in registers).
+__device__ __noinline__ double2 sincos2(double a)
+{
+    double sn, cs;
+    sincos(a, &sn, &cs);
+    return make_double2(sn, cs);
+}
+
+__device__ __noinline__ double atan2_ool(double y, double x) { return atan2(y, x); }
+
+// (sin, cos) of ssa((atan2(dy, dx) - alpha) - off): the bearing pattern of env:695-698, 724-727, 752-763
+__device__ __noinline__ double2 bearing_sincos(double dy, double dx, double alpha, double off)
+{
+    const double ang = ssa((atan2(dy, dx) - alpha) - off);
+    double sn, cs;
+    sincos(ang, &sn, &cs);
+    return make_double2(sn, cs);
+}
+
+// (atan2(s, c) + 2 pi) % (2 pi): the angle decode of env:435, 444-445, 482
+__device__ __noinline__ double atan2_mod2pi(double sn, double cs)
+{
+    return py_mod_pos(atan2(sn, cs) + D2D_TWO_PI, D2D_TWO_PI);
+}
+
 // ---------------------------------------------------------------------------
 // Philox4x32-10 counter-based stream (reset sampling, random actions)
 // ---------------------------------------------------------------------------
@@ -489,9 +516,8 @@ __device__ __forceinline__ void store_state(const D2dParams &p, int64_t i, const
 // Drone.__init__ (Drone.py:9-95): three bodies at rest, impulses cleared.
 __device__ __forceinline__ void spawn(EnvState &s, const D2dConst &c, double x, double y, double angle)
 {
-    double sn, cs, sn2, cs2;
-    sincos(angle, &sn, &cs);
-    sincos(angle + D2D_PI, &sn2, &cs2);
+    const double2 sc1 = sincos2(angle), sc2 = sincos2(angle + D2D_PI);
+    const double sn = sc1.x, cs = sc1.y, sn2 = sc2.x, cs2 = sc2.y;
     s.px[0] = x; s.py[0] = y;
     s.px[1] = cs2 * c.R + x; s.py[1] = sn2 * c.R + y;     // Drone.py:37
     s.px[2] = cs * c.R + x; s.py[2] = sn * c.R + y;       // Drone.py:51
@@ -519,8 +545,8 @@ __device__ __forceinline__ void physics_step(EnvState &s, const D2dConst &c, dou
     // cpBodyApplyForceAtLocalPoint on the frame, transform of the CURRENT pose
     double fx, fy, tq;
     {
-        double ry, rx;
-        sincos(s.an[0], &ry, &rx);
+        const double2 sc = sincos2(s.an[0]);
+        const double ry = sc.x, rx = sc.y;
         const double fwxL = -ry * FL, fwyL = rx * FL, fwxR = -ry * FR, fwyR = rx * FR;
         const double rLx = (rx * -c.R + s.px[0]) - s.px[0], rLy = (ry * -c.R + s.py[0]) - s.py[0];
         const double rRx = (rx * c.R + s.px[0]) - s.px[0], rRy = (ry * c.R + s.py[0]) - s.py[0];
@@ -535,7 +561,8 @@ __device__ __forceinline__ void physics_step(EnvState &s, const D2dConst &c, dou
         s.px[b] = s.px[b] + s.vx[b] * dt;
         s.py[b] = s.py[b] + s.vy[b] * dt;
         s.an[b] = s.an[b] + s.om[b] * dt;
-        sincos(s.an[b], &rs[b], &rc[b]);
+        const double2 sc = sincos2(s.an[b]);
+        rs[b] = sc.x; rc[b] = sc.y;
     }
     rc0 = rc[0]; rs0 = rs[0];
 
@@ -727,10 +754,9 @@ __device__ __forceinline__ void observe(const V &v, const D2dConst &c, EnvState 
     for (int j = 0; j < 3; j++) {
         double dn = 1.0, sa = 0.0, ca = 0.0;
         if (nr.idx[j] >= 0) {
-            double ang = atan2(y - nr.oy[j], x - nr.ox[j]);
-            ang = ssa(ang - alpha - D2D_PI);
+            const double2 sc = bearing_sincos(y - nr.oy[j], x - nr.ox[j], alpha, D2D_PI);
             dn = m1to1(nr.d[j], 0.0, c.diag);
-            sincos(ang, &sa, &ca);
+            sa = sc.x; ca = sc.y;
         }
         put(8 + 3 * j, dn); put(9 + 3 * j, sa); put(10 + 3 * j, ca);
         if (j == 0) { ax.o8 = dn; ax.o9 = sa; ax.o10 = ca; }
@@ -739,8 +765,8 @@ __device__ __forceinline__ void observe(const V &v, const D2dConst &c, EnvState 
 
     // env:723-727
     {
-        const double va = ssa(atan2(s.vy[0], s.vx[0]) - alpha);
-        sincos(va, &ax.o17, &ax.o18);
+        const double2 sc = bearing_sincos(s.vy[0], s.vx[0], alpha, 0.0);
+        ax.o17 = sc.x; ax.o18 = sc.y;
         put(17, ax.o17); put(18, ax.o18);
     }
 
@@ -766,16 +792,14 @@ __device__ __forceinline__ void observe(const V &v, const D2dConst &c, EnvState 
     // env:752-763: R_w_b rotates by +alpha (transformations.py:9-11)
     {
         const double dx = lx - x, dy = ly - y;
-        const double ang = ssa(atan2(rs0 * dx + rc0 * dy, rc0 * dx - rs0 * dy) - alpha);
-        sincos(ang, &ax.o23, &ax.o24);
+        const double2 sc = bearing_sincos(rs0 * dx + rc0 * dy, rc0 * dx - rs0 * dy, alpha, 0.0);
+        ax.o23 = sc.x; ax.o24 = sc.y;
         put(23, ax.o23); put(24, ax.o24);
     }
     {
         const double dx = cx - x, dy = cy - y;
-        const double ang = ssa(atan2(rs0 * dx + rc0 * dy, rc0 * dx - rs0 * dy) - alpha);
-        double sa, ca;
-        sincos(ang, &sa, &ca);
-        put(25, sa); put(26, ca);
+        const double2 sc = bearing_sincos(rs0 * dx + rc0 * dy, rc0 * dx - rs0 * dy, alpha, 0.0);
+        put(25, sc.x); put(26, sc.y);
     }
 }
 
@@ -797,14 +821,14 @@ __device__ __forceinline__ void reward_and_done(const D2dConst &c, EnvState &s, 
     const double alpha = o.o3 * D2D_PI;
     const double tdx = invm1to1(o.o4, 0.0, W), tdy = invm1to1(o.o5, 0.0, H);
     const double pos_x = invm1to1(o.o6, 0.0, W), pos_y = invm1to1(o.o7, 0.0, H);
-    const double vel_angle = py_mod_pos(atan2(o.o17 * D2D_PI, o.o18 * D2D_PI) + D2D_TWO_PI, D2D_TWO_PI);
+    const double vel_angle = atan2_mod2pi(o.o17 * D2D_PI, o.o18 * D2D_PI);
     const double cpx = invm1to1(o.o19, 0.0, W), cpy = invm1to1(o.o20, 0.0, H);
-    const double la_angle = py_mod_pos(atan2(o.o23, o.o24) + D2D_TWO_PI, D2D_TWO_PI);
+    const double la_angle = atan2_mod2pi(o.o23, o.o24);
 
     double lambda_PA = 1.0, lambda_CA = 1.0, r_CA = 0.0, d1 = CUDART_INF;
     if (has_obstacles) {                                          // env:462-523
         d1 = invm1to1(o.o8, 0.0, c.diag);
-        const double obs_angle = py_mod_pos(atan2(o.o9, o.o10) + D2D_TWO_PI, D2D_TWO_PI);
+        const double obs_angle = atan2_mod2pi(o.o9, o.o10);
         const double angle_diff =
             fabs((py_mod_pos(obs_angle - vel_angle + D2D_PI, D2D_TWO_PI) - D2D_PI) * (180.0 / D2D_PI));
         const double DR = c.danger_range, DA = c.danger_angle, kk = c.k_ca;
@@ -977,8 +1001,8 @@ __device__ __noinline__ ResetOut reset_env(const D2dParams &p, int64_t i, int ep
     us_s[0] = 0.0;
     for (int k = 1; k < N; k++) {
         const double az = rng.uniform(az_lo, az_hi);
-        double sn, cs;
-        sincos(az, &sn, &cs);
+        const double2 sc = sincos2(az);
+        const double sn = sc.x, cs = sc.y;
         const double nx = xb + c.seg_len * cs, ny = yb + c.seg_len * sn;
         const double ddx = nx - xb, ddy = ny - yb;
         u_cur = u_prev + sqrt(ddx * ddx + ddy * ddy);
