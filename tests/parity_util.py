@@ -75,7 +75,7 @@ def oracle_config_from(env):
         AA_angle=c.AA_angle, AA_band=c.AA_band, rew_AA=c.rew_AA, use_Lambda=c.use_Lambda, n_steps=c.n_steps)
 
 
-def run_parity(pkg, mode, scenario, n_envs, n_steps, seed=0, action_scale=1.0, inject_spawn=None, **kwargs):
+def run_parity(pkg, mode, scenario, n_envs, n_rounds, seed=0, action_scale=1.0, inject_spawn=None, **kwargs):
     """Step `n_envs` environments for `n_steps` on the GPU and in the oracle; returns error statistics."""
     import torch
     env = pkg.Drone2dVecEnv(n_envs, seed=seed, info_mode="episode", mode=mode, scenario=scenario, **kwargs)
@@ -103,7 +103,7 @@ def run_parity(pkg, mode, scenario, n_envs, n_steps, seed=0, action_scale=1.0, i
              max_u_err=0.0, max_reward_err=0.0, flag_mismatch=0, nearest_mismatch=0, nfev_mismatch=0,
              u_gt_1e9=0, env_steps=0, episodes=0, max_f32_obs_err=0.0, max_ape_err=0.0, max_reset_obs_err=0.0,
              reset_obs_checked=0)
-    for t in range(n_steps):
+    for t in range(n_rounds):
         actions = (rng.uniform(-1, 1, (n_envs, 2)) * action_scale).astype(np.float32)
         env.step_device(torch.from_numpy(actions).to(env.device))
         g_obs64 = env.obs64.cpu().numpy()

@@ -11,11 +11,11 @@ sys.path.insert(0, os.path.join(REPO, "tests"))
 pkg = importlib.import_module("drone_2d_custom_gym_env_for_reinforcement_learning_b200")
 from parity_util import run_parity  # noqa: E402
 
-for cfg in [dict(mode="test", scenario="corridor", n_envs=256, n_steps=64),
-            dict(mode="test", scenario="S_corridor", n_envs=256, n_steps=64),
-            dict(mode="test", scenario="large", n_envs=256, n_steps=64),
-            dict(mode="curriculum", scenario="stage_1", n_envs=256, n_steps=48),
-            dict(mode="curriculum", scenario="stage_5", n_envs=256, n_steps=48)]:
+for cfg in [dict(mode="test", scenario="corridor", n_envs=256, n_rounds=64),
+            dict(mode="test", scenario="S_corridor", n_envs=256, n_rounds=64),
+            dict(mode="test", scenario="large", n_envs=256, n_rounds=64),
+            dict(mode="curriculum", scenario="stage_1", n_envs=256, n_rounds=48),
+            dict(mode="curriculum", scenario="stage_5", n_envs=256, n_rounds=48)]:
     t = time.time()
     res = run_parity(pkg, seed=1, **cfg)
     print(json.dumps({"cfg": cfg, "res": res, "s": round(time.time() - t, 1)}), flush=True)
