@@ -47,3 +47,19 @@ def test_gpu_and_oracle_closed_loops_agree():
         sigma = np.sqrt(max(pc * (1 - pc), 0.02) / n_cpu + max(pg * (1 - pg), 0.02) / n_gpu)
         assert abs(pg - pc) <= 4 * sigma, (key, pg, pc, sigma)
     assert abs(g["env_steps"].mean() - c["env_steps"].mean()) <= 0.08 * c["env_steps"].mean()
+
+
+def test_run_test_writes_reference_artifacts(tmp_path):
+    """The reference's test mode end to end: 100 episodes, files in the Tests/agent_<nr>/test_<k>/<scenario>/ layout."""
+    ev = importlib.import_module(PKG + ".evaluate")
+    d, res = ev.run_test("ppo_agents/PFCA_see_3_obs_19_90.zip", "corridor", run_n_times=100, out_root=str(tmp_path / "Tests"),
+                         seed=3, weights_path=os.path.join(GOLDEN, "agent_19_policy.npz"))
+    assert d.endswith(os.path.join("agent_19", "test_0", "corridor"))
+    t = np.load(os.path.join(d, "time_spent.npy"))
+    fp = json.load(open(os.path.join(d, "flight_paths")))
+    assert t.shape == (100,) and len(fp) == 100
+    assert all(len(fp[i]) == t[i] for i in range(100))                 # one [x, H-y] per step until done
+    assert all(0 <= p[0] <= 1400 for p in fp[0])
+    txt = open(os.path.join(d, "corridor_19_results.txt")).read()
+    assert "Successes: %d" % int(res["n_successful_runs"].sum()) in txt
+    check_against_fixture(res, FIX["corridor"], 100, "corridor/run_test")
