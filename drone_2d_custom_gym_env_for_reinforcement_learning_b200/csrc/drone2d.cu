@@ -6,6 +6,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -612,8 +613,23 @@ int d2d_create(const d2d_config *cfg, int64_t n_envs, int64_t env_id_base, uint6
     // refill capacity per stage: one lane per 16 envs (a larger backlog is handled by striding over
     // the queue).  Tasks are dealt round-robin over the refill WARPS so that each warp carries only
     // a few lanes: the sampling loops have data-dependent trip counts and a warp runs for the
-    // maximum over its lanes.
-    p.refill_blocks = (int)((L.n + 16 * D2D_BLOCK - 1) / (16 * D2D_BLOCK));
+    // maximum over its lanes.  When the main blocks alone fit in one wave, the refill blocks are
+    // capped so that the whole grid still does (a second wave would double the step time).
+    {
+        int want = (int)((L.n + 16 * D2D_BLOCK - 1) / (16 * D2D_BLOCK));
+        int occ = 0, sms = 0;
+        cudaError_t oe = (cfg->mode == D2D_MODE_CURRICULUM)
+                             ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, d2d_step_kernel<true>, D2D_BLOCK, 0)
+                             : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, d2d_step_kernel<false>, D2D_BLOCK, 0);
+        if (oe == cudaSuccess) oe = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+        if (oe == cudaSuccess && occ > 0 && sms > 0) {
+            const int64_t slots = (int64_t)occ * sms, main_blocks = (L.n + D2D_BLOCK - 1) / D2D_BLOCK;
+            if (slots > main_blocks + 2) want = (int)std::min<int64_t>(want, (slots - main_blocks) / 2);
+        } else {
+            cudaGetLastError();
+        }
+        p.refill_blocks = want < 1 ? 1 : want;
+    }
     if (L.per_env_tables) {
         p.us = (double *)(base + L.off_us); p.wps = (double2 *)(base + L.off_wps);
         p.pa = (double2 *)(base + L.off_pa); p.pb = (double2 *)(base + L.off_pb); p.pc = (double2 *)(base + L.off_pc);
