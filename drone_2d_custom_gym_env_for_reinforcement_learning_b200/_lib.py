@@ -22,7 +22,7 @@ EXPORTS = [
     "d2d_abi_version", "d2d_last_error", "d2d_default_config", "d2d_state_bytes", "d2d_create", "d2d_destroy",
     "d2d_set_scenario", "d2d_set_tables", "d2d_get_tables", "d2d_reset", "d2d_step", "d2d_step_host",
     "d2d_set_taps", "d2d_get_state", "d2d_set_state", "d2d_episode_stats", "d2d_episode_stats_dev",
-    "d2d_debug_closest_u", "d2d_debug_role_cycles", "d2d_launch_count",
+    "d2d_debug_closest_u", "d2d_debug_role_cycles", "d2d_launch_count", "d2d_set_stage", "d2d_gae",
 ]
 
 
@@ -80,6 +80,8 @@ def load():
     L.d2d_episode_stats_dev.argtypes = [vp, C.POINTER(vp)]
     L.d2d_debug_closest_u.argtypes = [vp, vp, vp, vp, vp]
     L.d2d_debug_role_cycles.argtypes = [vp, C.POINTER(C.c_uint64), i32]
+    L.d2d_set_stage.argtypes = [vp, i32, C.c_double]
+    L.d2d_gae.argtypes = [vp, vp, vp, vp, vp, i32, i64, C.c_float, C.c_float, vp, vp, vp]
     L.d2d_launch_count.argtypes = [vp]
     L.d2d_launch_count.restype = i64
     for name in EXPORTS:

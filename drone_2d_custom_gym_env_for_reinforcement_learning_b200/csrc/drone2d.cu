@@ -436,6 +436,31 @@ __global__ void d2d_pack_tables_kernel(const D2dParams p, double *wps, double *u
     }
 }
 
+// Generalised advantage estimation over a device-resident rollout [T][N] (SB3
+// RolloutBuffer.compute_returns_and_advantage): one lane per environment walks the time axis
+// backwards; every access is coalesced over N.  Memory-bound: 5 floats read + 2 written per (t, n).
+__global__ void d2d_gae_kernel(const float *__restrict__ rewards, const float *__restrict__ values,
+                               const uint8_t *__restrict__ episode_starts, const float *__restrict__ last_values,
+                               const uint8_t *__restrict__ last_dones, int T, int64_t N, float gamma, float lam,
+                               float *__restrict__ advantages, float *__restrict__ returns)
+{
+    const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    float next_value = last_values[n];
+    float next_non_terminal = 1.0f - (float)(last_dones[n] != 0);
+    float gae = 0.0f;
+    for (int t = T - 1; t >= 0; t--) {
+        const int64_t k = (int64_t)t * N + n;
+        const float v = values[k];
+        const float delta = rewards[k] + gamma * next_value * next_non_terminal - v;
+        gae = delta + gamma * lam * next_non_terminal * gae;
+        advantages[k] = gae;
+        returns[k] = gae + v;
+        next_value = v;
+        next_non_terminal = 1.0f - (float)(episode_starts[k] != 0);
+    }
+}
+
 // ===========================================================================
 // host side: handle + C ABI
 // ===========================================================================
@@ -898,6 +923,31 @@ int d2d_debug_closest_u(d2d_env *e, const double *pos_dev, double *u_dev, int32_
     if (e->cfg.mode == D2D_MODE_CURRICULUM) d2d_closest_u_kernel<true><<<grid, D2D_BLOCK, 0, st>>>(e->p, pos_dev, u_dev, nfev_dev);
     else d2d_closest_u_kernel<false><<<grid, D2D_BLOCK, 0, st>>>(e->p, pos_dev, u_dev, nfev_dev);
     e->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return D2D_OK;
+}
+
+int d2d_set_stage(d2d_env *e, int stage, double spawn_chance)
+{
+    if (!e) return fail(D2D_EINVAL, "handle is NULL");
+    if (e->cfg.mode != D2D_MODE_CURRICULUM) return fail(D2D_ESTATE, "stages exist only in curriculum mode");
+    if (stage < 1 || stage > 5) return fail(D2D_EINVAL, "stage must be 1..5");
+    e->cfg.stage = stage; e->cfg.stage_spawn_chance = spawn_chance;
+    e->p.c.stage = stage; e->p.c.spawn_chance = spawn_chance;
+    return D2D_OK;
+}
+
+int d2d_gae(const float *rewards_dev, const float *values_dev, const uint8_t *episode_starts_dev,
+            const float *last_values_dev, const uint8_t *last_dones_dev, int n_steps, int64_t n_envs, float gamma,
+            float gae_lambda, float *advantages_dev, float *returns_dev, void *stream)
+{
+    if (!rewards_dev || !values_dev || !episode_starts_dev || !last_values_dev || !last_dones_dev || !advantages_dev ||
+        !returns_dev)
+        return fail(D2D_EINVAL, "NULL argument");
+    if (n_steps < 1 || n_envs < 1) return fail(D2D_EINVAL, "n_steps and n_envs must be >= 1");
+    d2d_gae_kernel<<<grid_for(n_envs, 256), 256, 0, (cudaStream_t)stream>>>(
+        rewards_dev, values_dev, episode_starts_dev, last_values_dev, last_dones_dev, n_steps, n_envs, gamma, gae_lambda,
+        advantages_dev, returns_dev);
     CUDA_TRY(cudaGetLastError());
     return D2D_OK;
 }

@@ -352,6 +352,16 @@ class Drone2dVecEnv:
         _lib.check(self._L.d2d_episode_stats(self._h, self._dp(out), 1 if reset else 0))
         return dict(zip(STATS_KEYS, out.tolist()))
 
+    def set_stage(self, stage=None, spawn_chance=None, sim_num=None):
+        """Curriculum scheduler: set the stage explicitly or from the training progress `sim_num`
+        (thresholds and obstacle-chance ramps of env:326-372)."""
+        if sim_num is not None:
+            stage, spawn_chance = stage_from_timesteps(int(sim_num))
+        if spawn_chance is None:
+            spawn_chance = {3: 0.6, 4: 1.0}.get(int(stage), 0.0)
+        _lib.check(self._L.d2d_set_stage(self._h, int(stage), float(spawn_chance)))
+        self.cfg.stage, self.cfg.stage_spawn_chance = int(stage), float(spawn_chance)
+
     def role_cycles(self, reset=True):
         """Profiling hook (d2d_debug_role_cycles): longest per-warp clock span per role / phase."""
         out = (C.c_uint64 * 24)()

@@ -161,6 +161,20 @@ int d2d_episode_stats_dev(d2d_env *env, double **stats_dev);
  * Env i uses its own path tables. */
 int d2d_debug_closest_u(d2d_env *env, const double *pos_dev, double *u_dev, int32_t *nfev_dev, void *stream);
 
+/* Curriculum scheduler hook: the reference derives the stage from the newest checkpoint file
+ * name every time an env is rebuilt (env:79-85, 326-372); here the trainer sets it explicitly.
+ * Takes effect for episodes sampled after the call (up to two already prefetched episodes per
+ * env keep the stage they were drawn with). */
+int d2d_set_stage(d2d_env *env, int stage, double spawn_chance);
+
+/* Generalised advantage estimation of a device-resident rollout (the step after `step` in the
+ * PPO loop the reference runs through SB3, main.py:190-208; SB3 RolloutBuffer semantics):
+ * rewards/values/advantages/returns float32 [n_steps][n_envs], episode_starts uint8
+ * [n_steps][n_envs], last_values float32 [n_envs], last_dones uint8 [n_envs].  One launch. */
+int d2d_gae(const float *rewards_dev, const float *values_dev, const uint8_t *episode_starts_dev,
+            const float *last_values_dev, const uint8_t *last_dones_dev, int n_steps, int64_t n_envs,
+            float gamma, float gae_lambda, float *advantages_dev, float *returns_dev, void *stream);
+
 /* Profiling hook: per-warp clock64() spans since the last reset, for role/phase r =
  * [0] a main lane's whole step, [1] the episode-sampling refill role, [2] the first-observation
  * refill role, [3] thrust + rigid-body solve, [4] obstacle pass, [5] observation incl. the
