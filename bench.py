@@ -39,6 +39,26 @@ ALGO_BYTES_SCENARIO = 657.0
 WORKLOAD = "stage_5 random obstacle field, 65536 envs/GPU, random actions, auto-reset"
 
 
+def _profiled_traffic(envs):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the step kernel, from the committed ncu
+    summary of this workload (profiles/*_step_kernel.json, written by tools/make_profile_summary.py)."""
+    try:
+        d = os.path.join(REPO, "profiles")
+        best = None
+        for f in sorted(os.listdir(d)):
+            if f.endswith("_step_kernel.json") and "interim" not in f:
+                best = os.path.join(d, f)
+        if best is None:
+            return None, None
+        with open(best) as fh:
+            j = json.load(fh)
+        if int(j.get("envs_per_launch", -1)) != int(envs):
+            return None, None
+        return float(j["dram_bytes_per_launch"]), os.path.basename(best)
+    except Exception:  # noqa: BLE001
+        return None, None
+
+
 def _peaks():
     try:
         with open(os.path.join(REPO, "MEASURED_PEAKS.json")) as f:
@@ -248,6 +268,7 @@ def run_ours(args):
         peak, peak_src = _peaks()
         per_launch_ms = ms / max(launches, 1)
         achieved = E * ALGO_BYTES_STAGE5 / (per_launch_ms / 1000.0) / 1e9
+        traffic, traffic_src = _profiled_traffic(E)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -260,7 +281,8 @@ def run_ours(args):
                     "d2h_bytes_per_step": E * (27 * 4 + 4 + 1), "steps": e2e_steps,
                     "api": "d2d_step_host (C ABI, page-locked host buffers)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src,
+                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": E * ALGO_BYTES_STAGE5,
                          "algorithmic_bytes_per_env_step": ALGO_BYTES_STAGE5,
                          "kernel": "d2d_step_kernel<true>", "kernel_ms": per_launch_ms},
             "episodes_finished": stats["episodes"],

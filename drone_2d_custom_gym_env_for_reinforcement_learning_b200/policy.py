@@ -61,6 +61,45 @@ class MlpActor:
         return mu.clamp_(-1.0, 1.0)
 
 
+class FusedActor:
+    """The same actor through the C ABI (`d2d_policy_act`): one hand-written kernel per call, Gaussian
+    noise from the environment handle's Philox stream -- no torch kernels between two env steps."""
+
+    def __init__(self, weights, env):
+        import ctypes as C
+        from . import _lib
+        self.env, self._L, self._C, self._lib = env, _lib.load(), C, _lib
+        w = [weights[k].detach().to(torch.float32).contiguous().cpu() for k in _KEYS]
+        nbytes = self._L.d2d_policy_weights_bytes()
+        host = torch.zeros(nbytes, dtype=torch.uint8)
+        _lib.check(self._L.d2d_policy_pack(w[0].data_ptr(), w[1].data_ptr(), w[2].data_ptr(), w[3].data_ptr(),
+                                           w[4].data_ptr(), w[5].data_ptr(), w[6].data_ptr(), host.data_ptr()))
+        self.packed = host.to(env.device)
+        self.actions = torch.empty((env.num_envs, 2), dtype=torch.float32, device=env.device)
+        self.step = 0
+
+    @classmethod
+    def load(cls, path, env):
+        return cls(load_actor_weights(path), env)
+
+    def predict(self, obs, deterministic=False, generator=None):
+        st = self._C.c_void_p(torch.cuda.current_stream(self.env.device).cuda_stream)
+        self._lib.check(self._L.d2d_policy_act(self.env._h, self.packed.data_ptr(), obs.data_ptr(), self.actions.data_ptr(),
+                                               0 if deterministic else 1, self.step, st))
+        self.step += 1
+        return self.actions
+
+    def rollout(self, n_steps, deterministic=False):
+        """n_steps closed-loop transitions enqueued from C (`d2d_rollout`): 2 launches per step, no host work."""
+        env = self.env
+        st = self._C.c_void_p(torch.cuda.current_stream(env.device).cuda_stream)
+        self._lib.check(self._L.d2d_rollout(env._h, self.packed.data_ptr(), env.obs.data_ptr(), self.actions.data_ptr(),
+                                            env.rewards.data_ptr(), env.dones.data_ptr(), int(n_steps),
+                                            0 if deterministic else 1, self.step, st))
+        self.step += int(n_steps)
+        return env.obs
+
+
 def rollout_one_episode_each(env, actor, deterministic=False, seed=0, max_steps=None):
     """Every env plays exactly ONE episode (the reference's test loop, main.py:258-287, one run per
     env): returns per-episode arrays success / fail / collision / APE / steps / total_reward."""

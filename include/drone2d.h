@@ -161,6 +161,28 @@ int d2d_episode_stats_dev(d2d_env *env, double **stats_dev);
  * Env i uses its own path tables. */
 int d2d_debug_closest_u(d2d_env *env, const double *pos_dev, double *u_dev, int32_t *nfev_dev, void *stream);
 
+/* Policy in the loop (the caller of step in the reference's test mode: `PPO.load` main.py:251,
+ * `model.predict` main.py:262): the SB3 MlpPolicy actor 27 -> 64 -> 64 -> 2 (tanh) evaluated on
+ * the device in ONE launch, so observations and actions never leave HBM/L2 between steps.
+ *   d2d_policy_weights_bytes  size of the packed weight block
+ *   d2d_policy_pack           HOST: pack `policy.pth` tensors (row-major float32: w0 [64][27], b0 [64],
+ *                             w1 [64][64], b1 [64], w2 [2][64], b2 [2], log_std [2]) into the block
+ *   d2d_policy_act            actions[n][2] = clip(mean(obs) + std * eps, -1, 1); eps ~ N(0,1) from the
+ *                             Philox stream keyed by (seed, global env id, policy_step) if stochastic,
+ *                             else 0 (deterministic `predict`).  packed_weights_dev: device copy of the block. */
+int d2d_policy_weights_bytes(void);
+int d2d_policy_pack(const float *w0, const float *b0, const float *w1, const float *b1, const float *w2,
+                    const float *b2, const float *log_std, void *packed_host);
+int d2d_policy_act(d2d_env *env, const void *packed_weights_dev, const float *obs_dev, float *actions_dev,
+                   int stochastic, uint64_t policy_step, void *stream);
+
+/* Closed-loop rollout without the host in the loop: n_steps x (d2d_policy_act, d2d_step with
+ * auto-reset) enqueued back to back on `stream`; obs_dev must hold the current observations on
+ * entry and holds the final ones on return.  Episode statistics accumulate in the handle. */
+int d2d_rollout(d2d_env *env, const void *packed_weights_dev, float *obs_dev, float *actions_dev,
+                float *reward_dev, uint8_t *done_dev, int n_steps, int stochastic, uint64_t policy_step0,
+                void *stream);
+
 /* Curriculum scheduler hook: the reference derives the stage from the newest checkpoint file
  * name every time an env is rebuilt (env:79-85, 326-372); here the trainer sets it explicitly.
  * Takes effect for episodes sampled after the call (up to two already prefetched episodes per

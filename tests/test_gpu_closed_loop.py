@@ -86,3 +86,42 @@ def test_rollout_collector_and_gae_kernel():
         env.step_device(None)
     assert env.get_tables()["n_obs"].max() >= 2
     env.close()
+
+
+def test_fused_policy_kernel_matches_torch_actor():
+    """d2d_policy_act (hand-written float32 MLP kernel) vs the torch float32 actor on real observations."""
+    import torch
+    pkg = importlib.import_module(PKG)
+    policy = importlib.import_module(PKG + ".policy")
+    n = 5000                                                   # partial last block
+    env = pkg.Drone2dVecEnv(n, seed=4, info_mode="none", mode="test", scenario="S_corridor")
+    obs = env.reset_device()
+    w = os.path.join(GOLDEN, "agent_19_policy.npz")
+    ref, fused = policy.MlpActor.load(w, env.device), policy.FusedActor.load(w, env)
+    for _ in range(30):
+        a_ref = ref.predict(obs, deterministic=True)
+        a_fused = fused.predict(obs, deterministic=True)
+        assert float((a_ref - a_fused).abs().max()) <= 2e-5
+        obs, _, _ = env.step_device(a_fused)
+    # stochastic: noise = std * N(0,1) from the Philox stream, different every call, clipped to the Box
+    mu = ref.mean(obs)
+    a1 = fused.predict(obs).clone()
+    a2 = fused.predict(obs).clone()
+    assert float((a1 - a2).abs().max()) > 0.1 and float(a1.abs().max()) <= 1.0
+    # where mean +- std lies inside the Box, clipping cannot affect the event |z| < 1: P = 68.3 %
+    safe = ((mu.abs() + ref.std) < 1.0)
+    z = (a1 - mu) / ref.std
+    frac = float(((z.abs() < 1.0) & safe).sum()) / float(safe.sum())
+    assert int(safe.sum()) > 1000 and abs(frac - 0.6827) < 0.03
+    assert abs(float((a1 > mu)[safe].float().mean()) - 0.5) < 0.03
+    env.close()
+
+
+def test_closed_loop_with_fused_policy_kernel():
+    pkg = importlib.import_module(PKG)
+    policy = importlib.import_module(PKG + ".policy")
+    env = pkg.Drone2dVecEnv(4096, seed=6, mode="test", scenario="large")
+    actor = policy.FusedActor.load(os.path.join(GOLDEN, "agent_19_policy.npz"), env)
+    res = policy.rollout_one_episode_each(env, actor, seed=1)
+    env.close()
+    check_against_fixture(res, FIX["large"], 4096, "large/fused")
