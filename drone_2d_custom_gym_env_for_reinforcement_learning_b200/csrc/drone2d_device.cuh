@@ -692,7 +692,7 @@ __device__ __forceinline__ bool scan_obstacles(const V &v, const D2dConst &c, do
                 const double dx = ox - x, dy = oy - y;
                 const double qx = rc0 * dx + rs0 * dy, qy = rc0 * dy - rs0 * dx;
                 const double ex = fmax(fabs(qx) - c.hw, 0.0), ey = fmax(fabs(qy) - c.hh, 0.0);
-                hit = hit || (sqrt(ex * ex + ey * ey) <= orad);
+                hit = hit || (ex * ex + ey * ey <= orad * orad);      // dist(centre, box) <= r, without the sqrt
             }
             // min over corners of sqrt(dx^2+dy^2) - r: the rounded operations are monotone,
             // so the minimum separates per axis and one sqrt suffices (bit-identical).
