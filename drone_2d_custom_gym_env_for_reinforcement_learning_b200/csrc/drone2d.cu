@@ -177,6 +177,18 @@ __global__ void __launch_bounds__(D2D_BLOCK, D2D_MIN_BLOCKS) d2d_step_kernel(con
     if (valid) {
         EnvState s;
         load_state(p, i, s);
+        if (PER_ENV) {
+            // Latency hiding for the closest-point search, issued while the solver runs:
+            // us[] of the live path goes global -> shared with cp.async (no registers held).
+            // (Pulling the polynomial rows into L2 here as well was measured: no gain.)
+            const int par0 = (s.flags & D2D_F_PARITY) ? 1 : 0;
+            const uint32_t base = (uint32_t)(par0 * D2D_MAX_WPS) * (uint32_t)p.np + (uint32_t)i;
+            for (int k = 0; k < c.n_wps; k++) {
+                const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&s_us[k * D2D_BLOCK + tid]);
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(p.us + base + (uint32_t)k * (uint32_t)p.np));
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        }
 
         float2 act;
         if (p.actions) {
@@ -197,10 +209,7 @@ __global__ void __launch_bounds__(D2D_BLOCK, D2D_MIN_BLOCKS) d2d_step_kernel(con
 
         float *row = &s_obs[tid * D2D_OBS_DIM];
         const int par = (s.flags & D2D_F_PARITY) ? 1 : 0;
-        if (PER_ENV) {
-            const uint32_t base = (uint32_t)(par * D2D_MAX_WPS) * (uint32_t)p.np + (uint32_t)i;
-            for (int k = 0; k < c.n_wps; k++) s_us[k * D2D_BLOCK + tid] = p.us[base + (uint32_t)k * (uint32_t)p.np];
-        }
+        if (PER_ENV) asm volatile("cp.async.wait_all;" ::: "memory");      // us[] column of this lane is in shared memory
         typename ViewOf<PER_ENV>::type v = ViewOf<PER_ENV>::make(p, &s_tab, i, s.n_obs, par, &s_us[tid]);
         Nearest nr;
         const bool hit = scan_obstacles(v, c, s.px[0], s.py[0], rc0, rs0, true, nr);
