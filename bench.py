@@ -197,8 +197,10 @@ def run_ours(args):
     env = pkg.Drone2dVecEnv(E, device=dev, seed=args.seed, env_id_base=rank * E, info_mode="none",
                             mode="curriculum", scenario="stage_5")
     env.reset_device()
-    # device-resident action ring: R distinct uniform(-1,1) batches, rotated every step
-    R = 16
+    # device-resident action ring: R distinct uniform(-1,1) batches, rotated every step.  R exceeds the
+    # typical episode length, so every env sees i.i.d. actions within an episode (a short ring repeats
+    # the same torque pattern and ends episodes ~2.5x sooner than action_space.sample() would).
+    R = 256
     g = torch.Generator(device=dev)
     g.manual_seed(1234 + rank)
     act_ring = (torch.rand((R, E, 2), device=dev, generator=g) * 2 - 1).contiguous()

@@ -1,0 +1,68 @@
+"""Size-independent properties at BASELINE.json's full sizes (65 536 envs per GPU), where the oracle
+is too slow to follow: determinism, conservation of the episode bookkeeping, sane ranges, and
+independence from how the batch is split."""
+import importlib
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+PKG = "drone_2d_custom_gym_env_for_reinforcement_learning_b200"
+N = 65536
+
+
+def _run(pkg, n, steps, seed, base=0, scenario="stage_5", mode="curriculum"):
+    import torch
+    env = pkg.Drone2dVecEnv(n, seed=seed, env_id_base=base, info_mode="none", mode=mode, scenario=scenario)
+    env.reset_device()
+    dones = torch.zeros((), dtype=torch.int64, device=env.device)
+    rsum = torch.zeros((), dtype=torch.float64, device=env.device)
+    for _ in range(steps):
+        obs, rew, done = env.step_device(None)          # in-kernel Philox actions keyed by (seed, global env id, step)
+        dones += done.sum()
+        rsum += rew.double().sum()
+        assert bool(torch.isfinite(obs).all()) and bool(torch.isfinite(rew).all())
+    st = env.get_state()
+    stats = env.episode_stats()
+    out = dict(state=st, stats=stats, dones=int(dones), rsum=float(rsum), obs=obs.cpu().numpy(), launches=env.launch_count)
+    env.close()
+    return out
+
+
+def test_full_batch_determinism_and_bookkeeping():
+    pkg = importlib.import_module(PKG)
+    a = _run(pkg, N, 160, seed=1)
+    b = _run(pkg, N, 160, seed=1)
+    assert np.array_equal(a["state"], b["state"])                      # bit-reproducible
+    for k, v in a["stats"].items():
+        # counts are exact; the float sums are accumulated with atomics (order-dependent rounding)
+        assert v == b["stats"][k] or abs(v - b["stats"][k]) <= 1e-11 * abs(v), k
+    s = a["stats"]
+    assert s["episodes"] == a["dones"] == a["state"][:, 35].sum()      # every done = one episode = one reset
+    assert s["n_successful_runs"] + s["n_failed_runs"] >= s["episodes"] > N // 4
+    assert abs(s["env_steps"] + a["state"][:, 32].sum() - 160 * N) < 0.5   # finished + running steps = all steps
+    assert a["launches"] == 162                                        # reset + one launch per step + the get_state gather
+    # reward bookkeeping: finished episodes' returns + running returns = sum of all rewards (float32 outputs)
+    total = s["total_reward"] + a["state"][:, 34].sum()
+    assert abs(total - a["rsum"]) <= 1e-5 * abs(total) + 1.0
+    st = a["state"]
+    assert np.all(np.abs(st[:, 4]) < np.pi / 2 + 0.3)                  # |alpha| ends episodes at pi/2 (one step of slack)
+    assert np.all(st[:, 32] <= 1100)
+    obs = a["obs"]
+    assert np.all(np.abs(obs[:, [9, 10, 12, 13, 15, 16, 17, 18, 23, 24, 25, 26]]) <= 1.0 + 1e-6)   # sines / cosines
+
+
+def test_full_batch_equals_two_half_batches():
+    pkg = importlib.import_module(PKG)
+    full = _run(pkg, N, 60, seed=2)
+    lo = _run(pkg, N // 2, 60, seed=2, base=0)
+    hi = _run(pkg, N // 2, 60, seed=2, base=N // 2)
+    assert np.array_equal(full["state"], np.concatenate([lo["state"], hi["state"]]))
+    assert full["stats"]["episodes"] == lo["stats"]["episodes"] + hi["stats"]["episodes"]
+
+
+def test_shared_table_scenario_full_batch():
+    pkg = importlib.import_module(PKG)
+    a = _run(pkg, N, 80, seed=3, scenario="S_corridor", mode="test")
+    assert a["stats"]["episodes"] == a["dones"] > 0
+    assert a["stats"]["n_collisions"] > 0                              # 58 obstacles around the path: random flight hits them

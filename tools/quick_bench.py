@@ -18,7 +18,8 @@ env = pkg.Drone2dVecEnv(E, seed=0, info_mode="none", mode=mode, scenario=scen)
 env.reset_device()
 g = torch.Generator(device=env.device)
 g.manual_seed(1)
-ring = (torch.rand((16, E, 2), device=env.device, generator=g) * 2 - 1).contiguous()
+R = 256
+ring = (torch.rand((R, E, 2), device=env.device, generator=g) * 2 - 1).contiguous()
 
 
 def timed(n, k0):
@@ -26,7 +27,7 @@ def timed(n, k0):
     torch.cuda.synchronize()
     ev0.record()
     for k in range(n):
-        env.step_device(ring[(k0 + k) % 16], terminal_obs=False)
+        env.step_device(ring[(k0 + k) % R], terminal_obs=False)
     ev1.record()
     torch.cuda.synchronize()
     return ev0.elapsed_time(ev1) / n * 1000.0
@@ -38,7 +39,7 @@ env.role_cycles()
 early = timed(10, 3)
 rc_early = env.role_cycles()
 for k in range(400):
-    env.step_device(ring[k % 16], terminal_obs=False)
+    env.step_device(ring[k % R], terminal_obs=False)
 env.role_cycles()
 steady = timed(400, 0)
 rc_steady = env.role_cycles()
