@@ -86,7 +86,7 @@ __device__ __forceinline__ void stage_sample(const D2dParams &p, int64_t e, doub
 {
     const int4 m = p.meta[e];
     const int target = m.z + 1;
-    const int par = (m.y & D2D_F_PARITY) ? 0 : 1;
+    const int par = 1;                              // staged episodes always live in table buffer 1
     const ResetOut ro = reset_env<PER_ENV>(p, e, target, par, us_s);
     p.stg_xy[e] = make_double2(ro.x, ro.y);
     p.stg_an[e] = make_double2(ro.angle, 0.0);
@@ -181,8 +181,7 @@ __global__ void __launch_bounds__(D2D_BLOCK, D2D_MIN_BLOCKS) d2d_step_kernel(con
             // Latency hiding for the closest-point search, issued while the solver runs:
             // us[] of the live path goes global -> shared with cp.async (no registers held).
             // (Pulling the polynomial rows into L2 here as well was measured: no gain.)
-            const int par0 = (s.flags & D2D_F_PARITY) ? 1 : 0;
-            const uint32_t base = (uint32_t)(par0 * D2D_MAX_WPS) * (uint32_t)p.np + (uint32_t)i;
+            const uint32_t base = (uint32_t)i;                  // live tables = buffer 0
             for (int k = 0; k < c.n_wps; k++) {
                 const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&s_us[k * D2D_BLOCK + tid]);
                 asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(p.us + base + (uint32_t)k * (uint32_t)p.np));
@@ -208,7 +207,7 @@ __global__ void __launch_bounds__(D2D_BLOCK, D2D_MIN_BLOCKS) d2d_step_kernel(con
         const long long t_phys = clock64();
 
         float *row = &s_obs[tid * D2D_OBS_DIM];
-        const int par = (s.flags & D2D_F_PARITY) ? 1 : 0;
+        const int par = 0;                                          // live tables = buffer 0
         if (PER_ENV) asm volatile("cp.async.wait_all;" ::: "memory");      // us[] column of this lane is in shared memory
         typename ViewOf<PER_ENV>::type v = ViewOf<PER_ENV>::make(p, &s_tab, i, s.n_obs, par, &s_us[tid]);
         Nearest nr;
@@ -271,20 +270,60 @@ __global__ void __launch_bounds__(D2D_BLOCK, D2D_MIN_BLOCKS) d2d_step_kernel(con
                 double nx, ny, na;
                 int n_obs, new_flags;
                 if (sm.x == next_ep) {
-                    // swap in the prefetched episode: flip the table buffer, take pose + first observation
+                    // swap in the prefetched episode: copy its tables from the staging buffer (1) into the
+                    // live buffer (0), take the spawn pose + first observation.  (Copying ~0.8 KB once per
+                    // episode keeps the per-step working set dense: with a per-env buffer flip, live and
+                    // staged rows of neighbouring envs share cache lines and the table traffic doubles.)
                     const double2 xy = p.stg_xy[i];
                     nx = xy.x; ny = xy.y; na = p.stg_an[i].x;
                     n_obs = sm.y;
-                    new_flags = D2D_F_INIT | (par ? 0 : D2D_F_PARITY) | (sm.z ? D2D_F_LATCHED : 0);
-                    const float *so = p.stg_obs + i * D2D_OBS_DIM;
+                    new_flags = D2D_F_INIT | (sm.z ? D2D_F_LATCHED : 0);
+                    if (PER_ENV) {
+                        const uint32_t np32 = (uint32_t)p.np, li = (uint32_t)i;
+                        const uint32_t sw = (uint32_t)D2D_MAX_WPS * np32, so = (uint32_t)D2D_MAX_OBS_ENV * np32;
+                        // batches of 4 table rows: 20 independent loads in flight, then 20 stores
+                        for (int k0 = 0; k0 < c.n_wps; k0 += 4) {
+                            double u4[4];
+                            double2 w4[4], a4[4], b4[4], c4[4];
 #pragma unroll
-                    for (int j = 0; j < D2D_OBS_DIM; j++) row[j] = so[j];
+                            for (int j = 0; j < 4; j++) {
+                                const int k = min(k0 + j, c.n_wps - 1);
+                                const uint32_t o = sw + (uint32_t)k * np32 + li;
+                                u4[j] = p.us[o]; w4[j] = p.wps[o]; a4[j] = p.pa[o]; b4[j] = p.pb[o]; c4[j] = p.pc[o];
+                            }
+#pragma unroll
+                            for (int j = 0; j < 4; j++) {
+                                const int k = k0 + j;
+                                if (k >= c.n_wps) break;
+                                const uint32_t o = (uint32_t)k * np32 + li;
+                                p.us[o] = u4[j]; p.wps[o] = w4[j]; p.pa[o] = a4[j]; p.pb[o] = b4[j]; p.pc[o] = c4[j];
+                            }
+                        }
+                        for (int k0 = 0; k0 < n_obs; k0 += 4) {
+                            double2 x4[4];
+                            double r4[4];
+#pragma unroll
+                            for (int j = 0; j < 4; j++) {
+                                const uint32_t o = so + (uint32_t)min(k0 + j, n_obs - 1) * np32 + li;
+                                x4[j] = p.obxy[o]; r4[j] = p.obr[o];
+                            }
+#pragma unroll
+                            for (int j = 0; j < 4; j++) {
+                                if (k0 + j >= n_obs) break;
+                                const uint32_t o = (uint32_t)(k0 + j) * np32 + li;
+                                p.obxy[o] = x4[j]; p.obr[o] = r4[j];
+                            }
+                        }
+                    }
+                    const float *sob = p.stg_obs + i * D2D_OBS_DIM;
+#pragma unroll
+                    for (int j = 0; j < D2D_OBS_DIM; j++) row[j] = sob[j];
                 } else {
                     // slot not ready (episode ended one step after the previous one, or state was
                     // injected): sample in the lane, into the live table buffer
                     const ResetOut ro = reset_env<PER_ENV>(p, i, next_ep, par, &s_us[PER_ENV ? tid : 0]);
                     nx = ro.x; ny = ro.y; na = ro.angle; n_obs = ro.n_obs;
-                    new_flags = D2D_F_INIT | (par ? D2D_F_PARITY : 0);
+                    new_flags = D2D_F_INIT;
                     new_flags |= first_observation<PER_ENV>(p, &s_tab, i, nx, ny, na, n_obs, par, row, nullptr, nullptr,
                                                             next_ep, &s_coef[tid]);
                 }
@@ -317,7 +356,7 @@ __global__ void __launch_bounds__(D2D_BLOCK, D2D_MIN_BLOCKS) d2d_step_kernel(con
         if (rows == D2D_BLOCK) {
             const float4 *src = reinterpret_cast<const float4 *>(s_obs);
             float4 *dst = reinterpret_cast<float4 *>(p.obs + base * D2D_OBS_DIM);
-            for (int k = tid; k < D2D_BLOCK * D2D_OBS_DIM / 4; k += D2D_BLOCK) dst[k] = src[k];
+            for (int k = tid; k < D2D_BLOCK * D2D_OBS_DIM / 4; k += D2D_BLOCK) __stcs(&dst[k], src[k]);   // streamed: read by the policy, not by the next step
         } else if (rows > 0) {
             float *dst = p.obs + base * D2D_OBS_DIM;
             for (int k = tid; k < rows * D2D_OBS_DIM; k += D2D_BLOCK) dst[k] = s_obs[k];
@@ -343,7 +382,7 @@ __global__ void __launch_bounds__(D2D_BLOCK) d2d_reset_kernel(const __grid_const
     const D2dConst &c = p.c;
     const int4 m = p.meta[i];
     const int episode = (m.y & D2D_F_INIT) ? m.z + 1 : 0;
-    const int par = (m.y & D2D_F_PARITY) ? 1 : 0;
+    const int par = 0;
     const ResetOut ro = reset_env<PER_ENV>(p, i, episode, par, &s_us[PER_ENV ? tid : 0]);
     const int latch = first_observation<PER_ENV>(p, &s_tab, i, ro.x, ro.y, ro.angle, ro.n_obs, par,
                                                  p.obs ? p.obs + i * D2D_OBS_DIM : nullptr,
@@ -351,7 +390,7 @@ __global__ void __launch_bounds__(D2D_BLOCK) d2d_reset_kernel(const __grid_const
                                                  p.info ? p.info + i * D2D_INFO_DOUBLES : nullptr, episode, &s_coef[tid]);
     EnvState s;
     spawn(s, c, ro.x, ro.y, ro.angle);
-    s.flags = D2D_F_INIT | (par ? D2D_F_PARITY : 0) | latch;
+    s.flags = D2D_F_INIT | latch;
     s.episode = episode; s.n_obs = ro.n_obs;
     store_state(p, i, s);
     stage_sample<PER_ENV>(p, i, &s_us[PER_ENV ? tid : 0]);
@@ -368,7 +407,7 @@ __global__ void d2d_closest_u_kernel(const __grid_constant__ D2dParams p, const 
     if (!PER_ENV) stage_shared_tables(p, &s_tab, tid, blockDim.x);
     __syncthreads();
     if (i >= p.n) return;
-    typename ViewOf<PER_ENV>::type v = ViewOf<PER_ENV>::make(p, &s_tab, i, 0, (p.meta[i].y & D2D_F_PARITY) ? 1 : 0);
+    typename ViewOf<PER_ENV>::type v = ViewOf<PER_ENV>::make(p, &s_tab, i, 0, 0);
     int nfev;
     PathCursor<typename ViewOf<PER_ENV>::type> pc(v, &s_coef[tid]);
     double bx, by;
@@ -400,7 +439,7 @@ __global__ void d2d_pack_state_kernel(const D2dParams p, double *blob, int to_bl
             s.an[k] = b[6 * k + 4]; s.om[k] = b[6 * k + 5];
         }
         for (int j = 0; j < 6; j++) { s.jx[j] = b[18 + 2 * j]; s.jy[j] = b[19 + 2 * j]; }
-        s.flags = D2D_F_INIT | (s.flags & D2D_F_PARITY) | (b[30] != 0.0 ? D2D_F_COLLIDED : 0) | (b[31] != 0.0 ? D2D_F_LATCHED : 0);
+        s.flags = D2D_F_INIT | (b[30] != 0.0 ? D2D_F_COLLIDED : 0) | (b[31] != 0.0 ? D2D_F_LATCHED : 0);
         s.steps = (int)b[32]; s.path_error = b[33]; s.total_reward = b[34]; s.episode = (int)b[35];
         store_state(p, i, s);
     }
@@ -412,7 +451,7 @@ __global__ void d2d_pack_tables_kernel(const D2dParams p, double *wps, double *u
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= p.n) return;
-    const int par = (p.meta[i].y & D2D_F_PARITY) ? 1 : 0;          // the live episode's buffer
+    const int par = 0;                                               // the live episode's buffer
     for (int k = 0; k < D2D_MAX_WPS; k++) {
         const int64_t r = (int64_t)(par * D2D_MAX_WPS + k) * p.np + i;
         double *w = wps + (i * D2D_MAX_WPS + k) * 2;

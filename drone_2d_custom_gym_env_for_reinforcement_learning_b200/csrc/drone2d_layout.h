@@ -30,7 +30,7 @@
 //
 // Per-env tables (curriculum mode only; rows of waypoint/segment index major so
 // that lanes reading the same row coalesce).  Two buffers per env: the live
-// episode and the staged one (meta flag D2D_F_PARITY selects the live buffer):
+// episode (buffer 0) and the staged one (buffer 1, copied into buffer 0 when it is swapped in):
 //   us   [2][MAX_WPS][N]        double
 //   wps  [2][MAX_WPS][N]        double2 (x, y)
 //   pa/pb/pc [2][MAX_WPS][N]    double2 (ax, ay) (bx, by) (cx, cy)   QPMI2D rows
@@ -105,7 +105,6 @@ static inline void d2d_make_layout(D2dLayout *L, int64_t n, int per_env_tables)
 #define D2D_F_LATCHED 2
 #define D2D_F_DONE 4      // terminal state kept (auto_reset == 0)
 #define D2D_F_INIT 8      // spawned at least once (episode counter valid)
-#define D2D_F_PARITY 16   // which of the two per-env table buffers holds the live episode
 
 // One shared scenario (test mode): path + circles, read-only, staged into shared memory.
 struct D2dSharedTables {
