@@ -280,7 +280,6 @@ __global__ void __launch_bounds__(D2D_BLOCK, D2D_MIN_BLOCKS) d2d_step_kernel(con
                     new_flags = D2D_F_INIT | (sm.z ? D2D_F_LATCHED : 0);
                     if (PER_ENV) {
                         const uint32_t np32 = (uint32_t)p.np, li = (uint32_t)i;
-                        const uint32_t sw = (uint32_t)D2D_MAX_WPS * np32, so = (uint32_t)D2D_MAX_OBS_ENV * np32;
                         // batches of 4 table rows: 20 independent loads in flight, then 20 stores
                         for (int k0 = 0; k0 < c.n_wps; k0 += 4) {
                             double u4[4];
@@ -288,8 +287,9 @@ __global__ void __launch_bounds__(D2D_BLOCK, D2D_MIN_BLOCKS) d2d_step_kernel(con
 #pragma unroll
                             for (int j = 0; j < 4; j++) {
                                 const int k = min(k0 + j, c.n_wps - 1);
-                                const uint32_t o = sw + (uint32_t)k * np32 + li;
-                                u4[j] = p.us[o]; w4[j] = p.wps[o]; a4[j] = p.pa[o]; b4[j] = p.pb[o]; c4[j] = p.pc[o];
+                                const uint32_t o = (uint32_t)k * np32 + li;
+                                u4[j] = p.us[p.stg_off8 + o]; w4[j] = p.wps[p.stg_off16 + o];
+                                a4[j] = p.pa[p.stg_off16 + o]; b4[j] = p.pb[p.stg_off16 + o]; c4[j] = p.pc[p.stg_off16 + o];
                             }
 #pragma unroll
                             for (int j = 0; j < 4; j++) {
@@ -304,8 +304,8 @@ __global__ void __launch_bounds__(D2D_BLOCK, D2D_MIN_BLOCKS) d2d_step_kernel(con
                             double r4[4];
 #pragma unroll
                             for (int j = 0; j < 4; j++) {
-                                const uint32_t o = so + (uint32_t)min(k0 + j, n_obs - 1) * np32 + li;
-                                x4[j] = p.obxy[o]; r4[j] = p.obr[o];
+                                const uint32_t o = (uint32_t)min(k0 + j, n_obs - 1) * np32 + li;
+                                x4[j] = p.obxy[p.stg_off16 + o]; r4[j] = p.obr[p.stg_off8 + o];
                             }
 #pragma unroll
                             for (int j = 0; j < 4; j++) {
@@ -451,9 +451,8 @@ __global__ void d2d_pack_tables_kernel(const D2dParams p, double *wps, double *u
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= p.n) return;
-    const int par = 0;                                               // the live episode's buffer
     for (int k = 0; k < D2D_MAX_WPS; k++) {
-        const int64_t r = (int64_t)(par * D2D_MAX_WPS + k) * p.np + i;
+        const int64_t r = (int64_t)k * p.np + i;
         double *w = wps + (i * D2D_MAX_WPS + k) * 2;
         double *x = xp + (i * D2D_MAX_WPS + k) * 3, *y = yp + (i * D2D_MAX_WPS + k) * 3;
         if (to_host) {
@@ -466,7 +465,7 @@ __global__ void d2d_pack_tables_kernel(const D2dParams p, double *wps, double *u
         }
     }
     for (int k = 0; k < D2D_MAX_OBS_ENV; k++) {
-        const int64_t r = (int64_t)(par * D2D_MAX_OBS_ENV + k) * p.np + i;
+        const int64_t r = (int64_t)k * p.np + i;
         double *o = obst + (i * D2D_MAX_OBS_ENV + k) * 3;
         if (to_host) {
             const double2 xy = p.obxy[r];
@@ -622,6 +621,10 @@ struct d2d_env {
     double *stats_dev;
     uint64_t step_index;
     int64_t launches;
+    // L2 residency control of the hot prefix of the state (see d2d_create)
+    void *l2_base;
+    size_t l2_bytes;
+    float l2_hit_ratio;
     // host-boundary staging (d2d_step_host)
     float *h_act, *h_obs, *h_rew;
     uint8_t *h_done;
@@ -789,6 +792,7 @@ int d2d_create(const d2d_config *cfg, int64_t n_envs, int64_t env_id_base, uint6
         p.us = (double *)(base + L.off_us); p.wps = (double2 *)(base + L.off_wps);
         p.pa = (double2 *)(base + L.off_pa); p.pb = (double2 *)(base + L.off_pb); p.pc = (double2 *)(base + L.off_pc);
         p.obxy = (double2 *)(base + L.off_obxy); p.obr = (double *)(base + L.off_obr);
+        p.stg_off8 = (uint32_t)(L.stg_delta / 8); p.stg_off16 = (uint32_t)(L.stg_delta / 16);
     }
     derive_constants(cfg, &p.c, seed, env_id_base);
     cudaError_t err = cudaMalloc(&e->shared_dev, sizeof(D2dSharedTables));
@@ -803,6 +807,25 @@ int d2d_create(const d2d_config *cfg, int64_t n_envs, int64_t env_id_base, uint6
     }
     p.shared = e->shared_dev;
     p.stats = e->stats_dev;
+    // Optional (D2D_L2_PERSIST=1): mark the hot prefix (dynamic state + live us/rows, touched once per
+    // step) as L2-persisting so that it survives from one step launch to the next.  Measured on B200 at
+    // 65 536 envs: 114.4 us/step with the window vs 112.3 us without -- off by default.
+    {
+        const char *env = getenv("D2D_L2_PERSIST");
+        int max_persist = 0, max_window = 0;
+        if ((env && env[0] == '1') &&
+            cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, device) == cudaSuccess &&
+            cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, device) == cudaSuccess &&
+            max_persist > 0 && max_window > 0) {
+            const size_t win = std::min<size_t>(L.hot_bytes, (size_t)max_window);
+            const size_t persist = std::min<size_t>(win, (size_t)max_persist);
+            if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, persist) == cudaSuccess) {
+                e->l2_base = state_dev; e->l2_bytes = win;
+                e->l2_hit_ratio = (float)std::min(1.0, (double)persist / (double)win);
+            }
+        }
+        cudaGetLastError();
+    }
     p.role_cycles = (unsigned long long *)(e->stats_dev + D2D_STATS_DOUBLES);
     e->tables_set = (cfg->mode == D2D_MODE_CURRICULUM);
     *out = e;
@@ -948,8 +971,21 @@ int d2d_step(d2d_env *e, const float *actions_dev, float *obs_dev, float *reward
     p.terminal_obs = terminal_obs_dev; p.auto_reset = auto_reset; p.step_index = e->step_index++;
     cudaStream_t st = (cudaStream_t)stream;
     const int grid = grid_for(p.n, D2D_BLOCK) + 2 * p.refill_blocks;
-    if (e->cfg.mode == D2D_MODE_CURRICULUM) d2d_step_kernel<true><<<grid, D2D_BLOCK, 0, st>>>(p);
-    else d2d_step_kernel<false><<<grid, D2D_BLOCK, 0, st>>>(p);
+    cudaLaunchConfig_t lc;
+    memset(&lc, 0, sizeof lc);
+    lc.gridDim = dim3((unsigned)grid); lc.blockDim = dim3(D2D_BLOCK); lc.dynamicSmemBytes = 0; lc.stream = st;
+    cudaLaunchAttribute attr[1];
+    if (e->l2_bytes) {
+        attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
+        attr[0].val.accessPolicyWindow.base_ptr = e->l2_base;
+        attr[0].val.accessPolicyWindow.num_bytes = e->l2_bytes;
+        attr[0].val.accessPolicyWindow.hitRatio = e->l2_hit_ratio;
+        attr[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        attr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        lc.attrs = attr; lc.numAttrs = 1;
+    }
+    if (e->cfg.mode == D2D_MODE_CURRICULUM) CUDA_TRY(cudaLaunchKernelEx(&lc, d2d_step_kernel<true>, p));
+    else CUDA_TRY(cudaLaunchKernelEx(&lc, d2d_step_kernel<false>, p));
     e->launches++;
     CUDA_TRY(cudaGetLastError());
     return D2D_OK;

@@ -184,19 +184,19 @@ struct EnvView {
     int par;                // table buffer (0/1) this view reads
     const double *us_s;     // optional shared-memory copy of this lane's us[] (element k at us_s[k * D2D_US_STRIDE])
     // 32-bit element offsets: 2 * 32 rows * np < 2^32 for np < 6.7e7 environments per GPU
-    __device__ __forceinline__ uint32_t wrow(int k) const { return (uint32_t)(par * D2D_MAX_WPS + k) * (uint32_t)p->np + (uint32_t)i; }
-    __device__ __forceinline__ uint32_t orow(int k) const { return (uint32_t)(par * D2D_MAX_OBS_ENV + k) * (uint32_t)p->np + (uint32_t)i; }
+    __device__ __forceinline__ uint32_t row8(int k) const { return (par ? p->stg_off8 : 0u) + (uint32_t)k * (uint32_t)p->np + (uint32_t)i; }
+    __device__ __forceinline__ uint32_t row16(int k) const { return (par ? p->stg_off16 : 0u) + (uint32_t)k * (uint32_t)p->np + (uint32_t)i; }
     __device__ __forceinline__ int n_wps() const { return p->c.n_wps; }
     __device__ __forceinline__ int n_obs() const { return nobs; }
-    __device__ __forceinline__ double us(int k) const { return us_s ? us_s[k * D2D_US_STRIDE] : p->us[wrow(k)]; }
-    __device__ __forceinline__ double2 wp(int k) const { return p->wps[wrow(k)]; }
-    __device__ __forceinline__ double2 pa(int r) const { return p->pa[wrow(r)]; }
-    __device__ __forceinline__ double2 pb(int r) const { return p->pb[wrow(r)]; }
-    __device__ __forceinline__ double2 pc(int r) const { return p->pc[wrow(r)]; }
+    __device__ __forceinline__ double us(int k) const { return us_s ? us_s[k * D2D_US_STRIDE] : p->us[row8(k)]; }
+    __device__ __forceinline__ double2 wp(int k) const { return p->wps[row16(k)]; }
+    __device__ __forceinline__ double2 pa(int r) const { return p->pa[row16(r)]; }
+    __device__ __forceinline__ double2 pb(int r) const { return p->pb[row16(r)]; }
+    __device__ __forceinline__ double2 pc(int r) const { return p->pc[row16(r)]; }
     __device__ __forceinline__ void obstacle(int k, double &x, double &y, double &r) const
     {
-        const double2 xy = p->obxy[orow(k)];
-        x = xy.x; y = xy.y; r = p->obr[orow(k)];
+        const double2 xy = p->obxy[row16(k)];
+        x = xy.x; y = xy.y; r = p->obr[row8(k)];
     }
 };
 
@@ -939,8 +939,8 @@ __device__ __forceinline__ int sample_obstacles(const D2dParams &p, EnvView &ev,
         double gx, gy, x, y;
         path_point_and_gradient(ev, u_obs, x, y, gx, gy);
         if (on_path) {
-            p.obxy[ev.orow(slot)] = make_double2(x, y);
-            p.obr[ev.orow(slot)] = size;
+            p.obxy[ev.row16(slot)] = make_double2(x, y);
+            p.obr[ev.row8(slot)] = size;
             slot++; made++;
             continue;
         }
@@ -948,8 +948,8 @@ __device__ __forceinline__ int sample_obstacles(const D2dParams &p, EnvView &ev,
         const double ox = x + dist * (gy * inv_g), oy = y + dist * (-gx * inv_g);
         const double ddx = ox - x, ddy = oy - y;
         if (sqrt(ddx * ddx + ddy * ddy) > size + 10.0) {
-            p.obxy[ev.orow(slot)] = make_double2(ox, oy);
-            p.obr[ev.orow(slot)] = size;
+            p.obxy[ev.row16(slot)] = make_double2(ox, oy);
+            p.obr[ev.row8(slot)] = size;
             slot++; made++;
         }
     }
@@ -996,8 +996,8 @@ __device__ __noinline__ ResetOut reset_env(const D2dParams &p, int64_t i, int ep
     // the reference inverts the 3x3 Vandermonde matrix -- same polynomial).
     double u_prev2 = 0.0, u_prev = 0.0, u_cur = 0.0;
     double xa = 0.0, ya = 0.0, xb = wx, yb = wy;                  // waypoints k-2, k-1
-    p.wps[ev.wrow(0)] = make_double2(wx, wy);
-    p.us[ev.wrow(0)] = 0.0;
+    p.wps[ev.row16(0)] = make_double2(wx, wy);
+    p.us[ev.row8(0)] = 0.0;
     us_s[0] = 0.0;
     for (int k = 1; k < N; k++) {
         const double az = rng.uniform(az_lo, az_hi);
@@ -1006,8 +1006,8 @@ __device__ __noinline__ ResetOut reset_env(const D2dParams &p, int64_t i, int ep
         const double nx = xb + c.seg_len * cs, ny = yb + c.seg_len * sn;
         const double ddx = nx - xb, ddy = ny - yb;
         u_cur = u_prev + sqrt(ddx * ddx + ddy * ddy);
-        p.wps[ev.wrow(k)] = make_double2(nx, ny);
-        p.us[ev.wrow(k)] = u_cur;
+        p.wps[ev.row16(k)] = make_double2(nx, ny);
+        p.us[ev.row8(k)] = u_cur;
         us_s[k * D2D_US_STRIDE] = u_cur;
         if (k >= 2) {
             const double u0 = u_prev2, u1 = u_prev, u2 = u_cur;
@@ -1016,9 +1016,9 @@ __device__ __noinline__ ResetOut reset_env(const D2dParams &p, int64_t i, int ep
             const double axx = (dx12 - dx01) / (u2 - u0), ayy = (dy12 - dy01) / (u2 - u0);
             const double bxx = dx01 - axx * (u0 + u1), byy = dy01 - ayy * (u0 + u1);
             const double cxx = xa - axx * u0 * u0 - bxx * u0, cyy = ya - ayy * u0 * u0 - byy * u0;
-            p.pa[ev.wrow(k - 2)] = make_double2(axx, ayy);
-            p.pb[ev.wrow(k - 2)] = make_double2(bxx, byy);
-            p.pc[ev.wrow(k - 2)] = make_double2(cxx, cyy);
+            p.pa[ev.row16(k - 2)] = make_double2(axx, ayy);
+            p.pb[ev.row16(k - 2)] = make_double2(bxx, byy);
+            p.pc[ev.row16(k - 2)] = make_double2(cxx, cyy);
         }
         xa = xb; ya = yb; xb = nx; yb = ny;
         u_prev2 = u_prev; u_prev = u_cur;

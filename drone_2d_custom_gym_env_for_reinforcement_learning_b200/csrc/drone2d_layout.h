@@ -31,10 +31,12 @@
 // Per-env tables (curriculum mode only; rows of waypoint/segment index major so
 // that lanes reading the same row coalesce).  Two buffers per env: the live
 // episode (buffer 0) and the staged one (buffer 1, copied into buffer 0 when it is swapped in):
-//   us   [2][MAX_WPS][N]        double
-//   wps  [2][MAX_WPS][N]        double2 (x, y)
-//   pa/pb/pc [2][MAX_WPS][N]    double2 (ax, ay) (bx, by) (cx, cy)   QPMI2D rows
-//   obxy [2][MAX_OBS_ENV][N]    double2 ; obr [2][MAX_OBS_ENV][N] double
+//   us   [MAX_WPS][N]        double
+//   pa/pb/pc [MAX_WPS][N]    double2 (ax, ay) (bx, by) (cx, cy)   QPMI2D rows
+//   obxy [MAX_OBS_ENV][N]    double2 ; obr [MAX_OBS_ENV][N] double
+//   wps  [MAX_WPS][N]        double2 (x, y)
+// The live block sits right behind the dynamic state (one contiguous "hot" prefix of the
+// allocation); the staged block has the same layout `stg_delta` bytes further on.
 #pragma once
 #include <stddef.h>
 #include <stdint.h>
@@ -62,6 +64,8 @@ struct D2dLayout {
     size_t off_stg_xy, off_stg_an, off_stg_meta, off_stg_obs, off_queue, off_qcount;
     size_t off_us, off_wps, off_pa, off_pb, off_pc, off_obxy, off_obr;
     size_t bytes;
+    size_t hot_bytes;      // leading bytes touched by every step (state + live us/rows)
+    size_t stg_delta;      // byte distance from a live per-env table to its staged copy
     int per_env_tables;
 };
 
@@ -74,12 +78,30 @@ static inline void d2d_make_layout(D2dLayout *L, int64_t n, int per_env_tables)
     L->per_env_tables = per_env_tables;
     size_t np = (size_t)L->np, o = 0;
     auto take = [&](size_t bytes) { size_t r = o; o = d2d_align_up(o + bytes, 256); return r; };
+    // hot region first (touched by every step): dynamic state, then the LIVE per-env tables with the
+    // most re-read arrays leading -- d2d_step marks [0, hot_bytes) as L2-persisting.
     L->off_pos = take(3 * np * 16);
     L->off_vel = take(3 * np * 16);
     L->off_ang = take(3 * np * 16);
     L->off_jacc = take(6 * np * 16);
     L->off_acc = take(np * 16);
     L->off_meta = take(np * 16);
+    L->off_us = L->off_wps = L->off_pa = L->off_pb = L->off_pc = L->off_obxy = L->off_obr = 0;
+    L->stg_delta = 0;
+    size_t live_begin = o;
+    if (per_env_tables) {
+        L->off_us = take((size_t)D2D_MAX_WPS * np * 8);
+        L->off_pa = take((size_t)D2D_MAX_WPS * np * 16);
+        L->off_pb = take((size_t)D2D_MAX_WPS * np * 16);
+        L->off_pc = take((size_t)D2D_MAX_WPS * np * 16);
+    }
+    L->hot_bytes = o;
+    if (per_env_tables) {
+        L->off_obxy = take((size_t)D2D_MAX_OBS_ENV * np * 16);
+        L->off_obr = take((size_t)D2D_MAX_OBS_ENV * np * 8);
+        L->off_wps = take((size_t)D2D_MAX_WPS * np * 16);
+    }
+    size_t live_end = o;
     L->off_last = take(2 * np * 16);
     L->off_stg_xy = take(np * 16);
     L->off_stg_an = take(np * 16);
@@ -87,15 +109,10 @@ static inline void d2d_make_layout(D2dLayout *L, int64_t n, int per_env_tables)
     L->off_stg_obs = take(np * D2D_OBS_DIM * 4);
     L->off_queue = take(3 * 3 * np * 4);       // A[3][np], B env[3][np], B target episode[3][np]
     L->off_qcount = take(256);
-    L->off_us = L->off_wps = L->off_pa = L->off_pb = L->off_pc = L->off_obxy = L->off_obr = 0;
     if (per_env_tables) {
-        L->off_us = take((size_t)2 * D2D_MAX_WPS * np * 8);
-        L->off_wps = take((size_t)2 * D2D_MAX_WPS * np * 16);
-        L->off_pa = take((size_t)2 * D2D_MAX_WPS * np * 16);
-        L->off_pb = take((size_t)2 * D2D_MAX_WPS * np * 16);
-        L->off_pc = take((size_t)2 * D2D_MAX_WPS * np * 16);
-        L->off_obxy = take((size_t)2 * D2D_MAX_OBS_ENV * np * 16);
-        L->off_obr = take((size_t)2 * D2D_MAX_OBS_ENV * np * 8);
+        // staged copy of the live table block, same internal layout, `stg_delta` bytes further on
+        size_t stg_begin = take(live_end - live_begin);
+        L->stg_delta = stg_begin - live_begin;
     }
     L->bytes = o;
 }
@@ -144,6 +161,7 @@ struct D2dParams {
     double *us;
     double2 *wps, *pa, *pb, *pc, *obxy;
     double *obr;
+    uint32_t stg_off8, stg_off16;   // element offsets (8- / 16-byte elements) from a live table to its staged copy
     double2 *stg_xy, *stg_an;
     int4 *stg_meta;
     float *stg_obs;
