@@ -279,73 +279,77 @@ __device__ __forceinline__ void path_gradient(const V &v, double u, double &dx, 
 }
 
 // ---------------------------------------------------------------------------
-// PathCursor: path_eval with the segment data of the last evaluation kept in
-// registers.  Brent's iterates stay inside one blending segment after the first
-// few golden-section steps, so most evaluations need no table access and no
-// segment search.  The arithmetic performed for a given u is IDENTICAL to
-// path_eval (same strict operations, same order) -- only the loads are cached.
-//   kind 0: single polynomial, first stretch   valid for us0 <= u <= us1
-//   kind 1: single polynomial, last stretch    valid for u >= us[-2] - 0.001
-//   kind 2: blend of rows n-1, n (n >= 1)      valid for us[n] < u <= us[n+1] and u < last_start
-//   kind 3: u < us0: blend of the LAST row and row 0 (Python index -1), n = 0
-// (first/last are disjoint for n_wps >= 4 with increasing us, which d2d_set_scenario /
-//  d2d_set_tables / the reset guarantee.)
+// PathCursor: path_eval with the data of the last visited path REGION cached (two polynomial
+// rows in a lane-private shared-memory column, the rest in registers), so that most evaluations
+// of the closest-point search need no table access and no segment search.  The arithmetic
+// performed for a given u is IDENTICAL to path_eval (same strict operations, same order) --
+// only the loads are cached.  Regions (n_wps = N >= 4, us increasing):
+//   START     u <= us[1]            rows (last, 0): u < us[0] blends them (Python index -1 quirk),
+//                                   us[0] <= u <= us[1] uses row 0 alone (first stretch)
+//   INTERIOR  us[n] < u <= us[n+1]  1 <= n <= N-4, blend of rows (n-1, n)
+//   END       u > us[N-3]           rows (N-4, N-3): blend below us[N-2] - 0.001, the last row alone
+//                                   from there on (last stretch and beyond the end)
+// START and END each merge a blended and a single-polynomial piece that share a row: the search
+// straddles exactly these junctions (the discontinuity at u = 0, the end of the path) whenever
+// the closest point is an end point, which is the slow, 45-evaluation case -- with separate
+// pieces every crossing was a cache miss, and in a warp some lane crossed on almost every trip.
 // ---------------------------------------------------------------------------
 template <class V>
 struct PathCursor {
     const V &v;
     int N;
-    double us0, us1, last_start;
-    // cached segment: valid for  u > vlo_x  &&  u >= vlo_i  &&  u <= vhi_i  &&  u < vhi_x
-    double vlo_x, vlo_i, vhi_i, vhi_x;
-    bool blend;
-    double lo, un1, len, rlen;
-    // the 2 x 3 polynomial rows of the cached segment live in a lane-private shared-memory
-    // column (coef[r * D2D_BLOCK], r = 0..5 = a1, b1, c1, a2, b2, c2): 24 registers fewer
-    // during the search, 6 conflict-free LDS.128 per evaluation instead.
+    double vlo_x, vhi_i;         // region validity: vlo_x < u <= vhi_i
+    double s_lo, s_hi;           // inside the region, s_lo <= u <= s_hi evaluates row 2 alone
+    double lo, un1, len, rlen;   // blending segment: us[n], us[n+1], their difference and its reciprocal
+    // the two polynomial rows live in a lane-private shared-memory column
+    // (coef[r * D2D_BLOCK], r = 0..5 = a1, b1, c1, a2, b2, c2): 24 registers fewer during the
+    // search, 6 conflict-free LDS.128 per evaluation instead.
     double2 *coef;
-    double inv_seg;      // (N-1)/L: initial guess of the segment index (any guess is corrected exactly)
+    double inv_seg;              // (N-1)/L: initial guess of the segment index (corrected exactly)
 
-    __device__ __forceinline__ PathCursor(const V &v_, double2 *coef_) : v(v_), N(v_.n_wps()), blend(false), coef(coef_)
+    __device__ __forceinline__ PathCursor(const V &v_, double2 *coef_) : v(v_), N(v_.n_wps()), coef(coef_)
     {
-        us0 = v.us(0); us1 = v.us(1);
-        last_start = S::sub(v.us(N - 2), 0.001);
-        inv_seg = (double)(N - 1) / v.us(N - 1);
-        vlo_x = vlo_i = CUDART_INF; vhi_i = vhi_x = -CUDART_INF;       // empty interval: first use locates
+        vlo_x = CUDART_INF; vhi_i = -CUDART_INF;                       // empty: the first use locates
+        s_lo = CUDART_INF; s_hi = -CUDART_INF;
         lo = un1 = len = rlen = 0.0;
+        inv_seg = (double)(N - 1) / v.us(N - 1);
     }
 
-    __device__ __forceinline__ bool hit(double u) const
+    __device__ __forceinline__ bool hit(double u) const { return (u > vlo_x) && (u <= vhi_i); }
+
+    __device__ __forceinline__ void load_rows(int r1, int r2)
     {
-        return (u > vlo_x) && (u >= vlo_i) && (u <= vhi_i) && (u < vhi_x);
+        coef[0] = v.pa(r1); coef[1 * D2D_BLOCK] = v.pb(r1); coef[2 * D2D_BLOCK] = v.pc(r1);
+        coef[3 * D2D_BLOCK] = v.pa(r2); coef[4 * D2D_BLOCK] = v.pb(r2); coef[5 * D2D_BLOCK] = v.pc(r2);
     }
 
     __device__ __forceinline__ void locate(double u)
     {
         const int rows = N - 2;
-        vlo_x = vlo_i = -CUDART_INF; vhi_i = vhi_x = CUDART_INF;
-        if (u >= us0 && u <= us1) {                                  // first stretch
-            blend = false; vlo_i = us0; vhi_i = us1;
-            coef[3 * D2D_BLOCK] = v.pa(0); coef[4 * D2D_BLOCK] = v.pb(0); coef[5 * D2D_BLOCK] = v.pc(0);
-        } else if (u >= last_start) {                                // last stretch (and beyond the end)
-            blend = false; vlo_i = last_start;
-            coef[3 * D2D_BLOCK] = v.pa(rows - 1); coef[4 * D2D_BLOCK] = v.pb(rows - 1); coef[5 * D2D_BLOCK] = v.pc(rows - 1);
-        } else {
+        const double us1 = v.us(1), usm3 = v.us(N - 3);
+        if (u <= us1) {                                              // START
+            lo = v.us(0); un1 = us1;
+            vlo_x = -CUDART_INF; vhi_i = us1;
+            s_lo = lo; s_hi = us1;
+            load_rows(rows - 1, 0);
+        } else if (u > usm3) {                                       // END
+            lo = usm3; un1 = v.us(N - 2);
+            vlo_x = usm3; vhi_i = CUDART_INF;
+            s_lo = S::sub(un1, 0.001); s_hi = CUDART_INF;
+            load_rows(rows - 2, rows - 1);
+        } else {                                                     // INTERIOR
             // get_u_index (predef_path.py:53-63) = number of us[k], k >= 1, below u: start from the
             // uniform-spacing guess and walk to the exact answer (0-1 steps on the reference's paths)
-            int n = min(max((int)(u * inv_seg), 0), N - 2);
-            while (n < N - 1 && u > v.us(n + 1)) n++;
-            while (n > 0 && !(u > v.us(n))) n--;
-            blend = true;
+            int n = min(max((int)(u * inv_seg), 1), N - 4);
+            while (n < N - 4 && u > v.us(n + 1)) n++;
+            while (n > 1 && !(u > v.us(n))) n--;
             lo = v.us(n); un1 = v.us(n + 1);
-            if (n == 0) { vhi_x = us0; }                             // u < us[0]: rows -1 (= last) and 0
-            else { vlo_x = lo; vhi_i = un1; vhi_x = last_start; }
-            len = S::sub(un1, lo);
-            rlen = S::div(1.0, len);
-            const int r1 = (n - 1 < 0) ? rows - 1 : n - 1;          // Python negative index
-            coef[0] = v.pa(r1); coef[1 * D2D_BLOCK] = v.pb(r1); coef[2 * D2D_BLOCK] = v.pc(r1);
-            coef[3 * D2D_BLOCK] = v.pa(n); coef[4 * D2D_BLOCK] = v.pb(n); coef[5 * D2D_BLOCK] = v.pc(n);
+            vlo_x = lo; vhi_i = un1;
+            s_lo = CUDART_INF; s_hi = -CUDART_INF;
+            load_rows(n - 1, n);
         }
+        len = S::sub(un1, lo);
+        rlen = S::div(1.0, len);
     }
 
     // x / len, correctly rounded, from the cached correctly rounded reciprocal (Markstein:
@@ -364,7 +368,7 @@ struct PathCursor {
         const double uu = S::mul(u, u);
         const double2 a2 = coef[3 * D2D_BLOCK], b2 = coef[4 * D2D_BLOCK], c2 = coef[5 * D2D_BLOCK];
         const double x2 = poly2(a2.x, b2.x, c2.x, u, uu), y2 = poly2(a2.y, b2.y, c2.y, u, uu);
-        if (!blend) { x = x2; y = y2; return; }
+        if (u >= s_lo && u <= s_hi) { x = x2; y = y2; return; }
         const double2 a1 = coef[0], b1 = coef[1 * D2D_BLOCK], c1 = coef[2 * D2D_BLOCK];
         const double mu_r = div_len(S::sub(u, lo));
         const double mu_f = div_len(S::sub(un1, u));
