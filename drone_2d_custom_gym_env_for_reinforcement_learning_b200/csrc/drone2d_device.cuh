@@ -409,19 +409,26 @@ __device__ __forceinline__ double closest_u(PathCursor<V> &pc, double px, double
         const double fu = S::sqrt(S::fma(dy, dy, S::mul(dx, dx)));
         if (num == 0) {
             fx = fu; ffulc = fu; fnfc = fu; bx = ex; by = ey;
-        } else if (fu <= fx) {
-            if (x >= xf) a = xf; else b = xf;
-            fulc = nfc; ffulc = fnfc;
-            nfc = xf; fnfc = fx;
-            xf = x; fx = fu; bx = ex; by = ey;
         } else {
-            if (x < xf) a = x; else b = x;
-            if ((fu <= fnfc) || (nfc == xf)) {
-                fulc = nfc; ffulc = fnfc;
-                nfc = x; fnfc = fu;
-            } else if ((fu <= ffulc) || (fulc == xf) || (fulc == nfc)) {
-                fulc = x; ffulc = fu;
-            }
+            // scipy's update rules (`if fu <= fx: ... else: ...`, _optimize.py:2393-2412) as one
+            // branch-free dataflow: the lanes of a warp take different branches on almost every
+            // trip, and the branchy form costs ~90 register moves per trip on top of both paths.
+            const bool better = (fu <= fx);
+            const bool right = (x >= xf);
+            const bool c1 = (fu <= fnfc) || (nfc == xf);                          // worse: new point becomes nfc
+            const bool c2 = (fu <= ffulc) || (fulc == xf) || (fulc == nfc);       // worse: new point becomes fulc
+            const bool shift = better || c1;                                      // (nfc, fnfc) -> (fulc, ffulc)
+            const double t = better ? xf : x;                                     // the new bracket end
+            const double na = (better == right) ? t : a;
+            const double nb = (better != right) ? t : b;
+            const double n_fulc = shift ? nfc : (c2 ? x : fulc);
+            const double n_ffulc = shift ? fnfc : (c2 ? fu : ffulc);
+            const double n_nfc = better ? xf : (c1 ? x : nfc);
+            const double n_fnfc = better ? fx : (c1 ? fu : fnfc);
+            a = na; b = nb;
+            fulc = n_fulc; ffulc = n_ffulc; nfc = n_nfc; fnfc = n_fnfc;
+            xf = better ? x : xf; fx = better ? fu : fx;
+            bx = better ? ex : bx; by = better ? ey : by;
         }
         num += 1;
         const double xm = S::mul(0.5, S::add(a, b));
