@@ -73,6 +73,9 @@ __device__ __forceinline__ double ssa(double a) { return py_mod_pos(a + D2D_PI, 
 __device__ __forceinline__ double m1to1(double v, double lo, double hi) { return 2.0 * (v - lo) / (hi - lo) - 1.0; }
 __device__ __forceinline__ double invm1to1(double v, double lo, double hi) { return (v + 1.0) * (hi - lo) / 2.0 + lo; }
 __device__ __forceinline__ double clipd(double v, double lo, double hi) { return v < lo ? lo : (v > hi ? hi : v); }
+// min / max of finite values (fmin/fmax carry NaN handling that costs ~8 instructions per call)
+__device__ __forceinline__ double min_f(double a, double b) { return (b < a) ? b : a; }
+__device__ __forceinline__ double max_f(double a, double b) { return (b > a) ? b : a; }
 
 // Out-of-line transcendentals: CUDA's double sincos/atan2 expand to ~150 instructions each at
 // every call site; the step calls them ~20 times, which made the kernel's hot path several times
@@ -463,7 +466,7 @@ __device__ __forceinline__ double closest_u(PathCursor<V> &pc, double px, double
             rat = S::mul(golden_mean, e);
         }
         // x = xf + (sign(rat) + (rat == 0)) * max(|rat|, tol1)
-        const double mag = fmax(fabs(rat), tol1);
+        const double mag = max_f(fabs(rat), tol1);
         x = S::add(xf, (rat < 0.0) ? -mag : mag);
     }
     nfev = num;
@@ -702,30 +705,38 @@ __device__ __forceinline__ bool scan_obstacles(const V &v, const D2dConst &c, do
             if (test_collision) {
                 const double dx = ox - x, dy = oy - y;
                 const double qx = rc0 * dx + rs0 * dy, qy = rc0 * dy - rs0 * dx;
-                const double ex = fmax(fabs(qx) - c.hw, 0.0), ey = fmax(fabs(qy) - c.hh, 0.0);
+                const double ex = max_f(fabs(qx) - c.hw, 0.0), ey = max_f(fabs(qy) - c.hh, 0.0);
                 hit = hit || (ex * ex + ey * ey <= orad * orad);      // dist(centre, box) <= r, without the sqrt
             }
             // min over corners of sqrt(dx^2+dy^2) - r: the rounded operations are monotone,
             // so the minimum separates per axis and one sqrt suffices (bit-identical).
             const double dxp = S::sub(cxp, ox), dxm = S::sub(cxm, ox);
             const double dyp = S::sub(cyp, oy), dym = S::sub(cym, oy);
-            const double qx2 = fmin(S::mul(dxp, dxp), S::mul(dxm, dxm));
-            const double qy2 = fmin(S::mul(dyp, dyp), S::mul(dym, dym));
+            const double qx2 = min_f(S::mul(dxp, dxp), S::mul(dxm, dxm));
+            const double qy2 = min_f(S::mul(dyp, dyp), S::mul(dym, dym));
             const double dist = S::sub(S::sqrt(S::add(qx2, qy2)), orad);
-            // stable insertion (strict <: ties keep the lower index first, like sorted())
+            // stable insertion (strict <: ties keep the lower index first, like sorted()); only
+            // (distance, index) travel through the insertion, the centres are re-read afterwards
             if (dist < nr.d[2]) {
                 if (dist < nr.d[1]) {
-                    nr.d[2] = nr.d[1]; nr.idx[2] = nr.idx[1]; nr.ox[2] = nr.ox[1]; nr.oy[2] = nr.oy[1];
+                    nr.d[2] = nr.d[1]; nr.idx[2] = nr.idx[1];
                     if (dist < nr.d[0]) {
-                        nr.d[1] = nr.d[0]; nr.idx[1] = nr.idx[0]; nr.ox[1] = nr.ox[0]; nr.oy[1] = nr.oy[0];
-                        nr.d[0] = dist; nr.idx[0] = k; nr.ox[0] = ox; nr.oy[0] = oy;
+                        nr.d[1] = nr.d[0]; nr.idx[1] = nr.idx[0];
+                        nr.d[0] = dist; nr.idx[0] = k;
                     } else {
-                        nr.d[1] = dist; nr.idx[1] = k; nr.ox[1] = ox; nr.oy[1] = oy;
+                        nr.d[1] = dist; nr.idx[1] = k;
                     }
                 } else {
-                    nr.d[2] = dist; nr.idx[2] = k; nr.ox[2] = ox; nr.oy[2] = oy;
+                    nr.d[2] = dist; nr.idx[2] = k;
                 }
             }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+        if (nr.idx[j] >= 0) {
+            double rr;
+            v.obstacle(nr.idx[j], nr.ox[j], nr.oy[j], rr);
         }
     }
     return hit;
