@@ -704,6 +704,8 @@ static void derive_constants(const d2d_config *g, D2dConst *c, uint64_t seed, in
     c->msum = c->minv_m + c->minv_f;
     c->bias_coef = -(1.0 - pow(0.0, g->dt)) / g->dt;          // error_bias = 0 (Drone.py:64)
     c->diag = sqrt(g->screen_x * g->screen_x + g->screen_y * g->screen_y);
+    c->r_vel = 1.0 / 2660.0; c->r_W = 1.0 / g->screen_x; c->r_H = 1.0 / g->screen_y; c->r_diag = 1.0 / c->diag;
+    c->r_omega = 1.0 / 11.7; c->r_pi = 1.0 / M_PI; c->r_DR = 1.0 / g->danger_range; c->r_PA = 1.0 / g->PA_band_edge;
     c->seed_lo = (uint32_t)seed; c->seed_hi = (uint32_t)(seed >> 32);
     c->env_id_base = env_id_base;
 }
@@ -881,6 +883,7 @@ static int launch_tables_kernel(d2d_env *e, double *wps, double *us, double *xp,
     const size_t b_n = n * 4, b_o = n * D2D_MAX_OBS_ENV * 3 * 8;
     char *buf = nullptr;
     const size_t total = b_w + b_u + 2 * b_p + b_o + d2d_align_up(b_n, 8);
+    CUDA_TRY(cudaDeviceSynchronize());          // steps may be in flight on a non-blocking stream
     CUDA_TRY(cudaMalloc(&buf, total));
     double *dw = (double *)buf, *du = (double *)(buf + b_w), *dx = (double *)(buf + b_w + b_u);
     double *dy = (double *)(buf + b_w + b_u + b_p), *dob = (double *)(buf + b_w + b_u + 2 * b_p);
@@ -919,8 +922,12 @@ int d2d_set_tables(d2d_env *e, const double *wps, const double *us, const double
     if (!e) return fail(D2D_EINVAL, "handle is NULL");
     if (e->cfg.mode != D2D_MODE_CURRICULUM) return fail(D2D_ESTATE, "per-env tables exist only in curriculum mode");
     if (!wps || !us || !xparams || !yparams || !n_obs || !obstacles) return fail(D2D_EINVAL, "NULL table pointer");
-    for (int64_t i = 0; i < e->lay.n; i++)
+    for (int64_t i = 0; i < e->lay.n; i++) {
         if (n_obs[i] < 0 || n_obs[i] > D2D_MAX_OBS_ENV) return fail(D2D_EINVAL, "n_obs[%lld] out of range", (long long)i);
+        for (int k = 1; k < e->cfg.n_wps; k++)
+            if (!(us[i * D2D_MAX_WPS + k] > us[i * D2D_MAX_WPS + k - 1]))
+                return fail(D2D_EINVAL, "us of env %lld must be strictly increasing", (long long)i);
+    }
     DeviceGuard guard(e->device);
     return launch_tables_kernel(e, (double *)wps, (double *)us, (double *)xparams, (double *)yparams, (int32_t *)n_obs,
                                 (double *)obstacles, 0);
@@ -1043,6 +1050,7 @@ static int state_transfer(d2d_env *e, double *host, int to_host)
     const int64_t n = e->lay.n;
     const size_t bytes = n * D2D_STATE_DOUBLES * sizeof(double);
     double *blob = nullptr;
+    CUDA_TRY(cudaDeviceSynchronize());          // steps may be in flight on a non-blocking stream
     CUDA_TRY(cudaMalloc(&blob, bytes));
     cudaError_t err = cudaSuccess;
     if (!to_host) err = cudaMemcpy(blob, host, bytes, cudaMemcpyHostToDevice);

@@ -149,6 +149,10 @@ struct D2dConst {
     double msum;                 // minv_m + minv_f
     double bias_coef;            // -(1 - pow(0, dt)) / dt
     double diag;                 // sqrt(W^2 + H^2)
+    // correctly rounded reciprocals of the constant divisors of the observation / reward (exact
+    // division by a constant in 3 FMAs, see div_const): 2660 (velocity range), W, H, diag, 11.7, pi,
+    // danger_range, PA_band_edge
+    double r_vel, r_W, r_H, r_diag, r_omega, r_pi, r_DR, r_PA;
     uint32_t seed_lo, seed_hi;
     int64_t env_id_base;
 };

@@ -91,8 +91,9 @@ class Drone2dVecEnv:
     Device-resident surface (no host copies): reset_device(), step_device().
 
     info_mode: "episode" (default) -> infos carry the reference's keys only for
-    envs that finished this step; "full" -> every env, every key of env:575-587
-    (slow for large N); "none" -> no per-env float64 taps at all (benchmarks).
+    envs that finished this step (all other entries are one shared empty dict: do
+    not mutate it); "full" -> every env, every key of env:575-587 (slow for large
+    N); "none" -> no per-env float64 taps at all (benchmarks).
     """
 
     metadata = {"render_modes": []}
