@@ -321,6 +321,7 @@ __global__ void __launch_bounds__(D2D_BLOCK, D2D_MIN_BLOCKS) d2d_step_kernel(con
                 } else {
                     // slot not ready (episode ended one step after the previous one, or state was
                     // injected): sample in the lane, into the live table buffer
+                    atomicAdd(&s_stats[15], 1.0);
                     const ResetOut ro = reset_env<PER_ENV>(p, i, next_ep, par, &s_us[PER_ENV ? tid : 0]);
                     nx = ro.x; ny = ro.y; na = ro.angle; n_obs = ro.n_obs;
                     new_flags = D2D_F_INIT;
@@ -362,7 +363,7 @@ __global__ void __launch_bounds__(D2D_BLOCK, D2D_MIN_BLOCKS) d2d_step_kernel(con
             for (int k = tid; k < rows * D2D_OBS_DIM; k += D2D_BLOCK) dst[k] = s_obs[k];
         }
     }
-    if (s_any_done && tid < 14) atomicAdd(&p.stats[tid], s_stats[tid]);
+    if (s_any_done && (tid < 14 || tid == 15)) atomicAdd(&p.stats[tid], s_stats[tid]);
 }
 
 // Drone2dEnv.reset() for all / masked envs: re-spawn + first observation, and prefetch of

@@ -21,7 +21,7 @@ INFO_KEYS = ("reward", "collision_avoidance_reward", "path_adherence", "path_pro
              "reach_end_reward", "agressive_alpha_reward", "env_steps", "dist_closest_obs")
 STATS_KEYS = ("episodes", "n_successful_runs", "n_failed_runs", "n_collisions", "env_steps", "APE", "total_reward",
               "reward", "collision_reward", "collision_avoidance_reward", "path_adherence", "path_progression",
-              "reach_end_reward", "agressive_alpha_reward", "steps_taken", "unused")
+              "reach_end_reward", "agressive_alpha_reward", "steps_taken", "inlane_resets")
 _EMPTY_INFO = {}
 
 

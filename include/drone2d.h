@@ -151,7 +151,8 @@ int d2d_set_state(d2d_env *env, const double *state_host);
  *   sum total_reward, then the sums of the LAST-step info terms that
  *   tensorboardlogger.py:80-88 averages: reward, collision_reward,
  *   collision_avoidance_reward, path_adherence, path_progression,
- *   reach_end_reward, agressive_alpha_reward; [14] = steps taken, [15] unused. */
+ *   reach_end_reward, agressive_alpha_reward; [14] = steps taken, [15] = auto-resets that could
+ *   not use a prefetched episode and sampled in the lane (diagnostic; ~5 per million episodes). */
 int d2d_episode_stats(d2d_env *env, double *stats_host, int reset_after);
 /* Device pointer of the same vector (for an NCCL all-reduce over ranks). */
 int d2d_episode_stats_dev(d2d_env *env, double **stats_dev);

@@ -41,6 +41,7 @@ def test_full_batch_determinism_and_bookkeeping():
     assert s["episodes"] == a["dones"] == a["state"][:, 35].sum()      # every done = one episode = one reset
     assert s["n_successful_runs"] + s["n_failed_runs"] >= s["episodes"] > N // 4
     assert abs(s["env_steps"] + a["state"][:, 32].sum() - 160 * N) < 0.5   # finished + running steps = all steps
+    assert s["inlane_resets"] <= 1e-4 * s["episodes"]               # (almost) every auto-reset used its prefetched episode
     assert a["launches"] == 162                                        # reset + one launch per step + the get_state gather
     # reward bookkeeping: finished episodes' returns + running returns = sum of all rewards (float32 outputs)
     total = s["total_reward"] + a["state"][:, 34].sum()
@@ -66,3 +67,26 @@ def test_shared_table_scenario_full_batch():
     a = _run(pkg, N, 80, seed=3, scenario="S_corridor", mode="test")
     assert a["stats"]["episodes"] == a["dones"] > 0
     assert a["stats"]["n_collisions"] > 0                              # 58 obstacles around the path: random flight hits them
+
+
+def test_long_run_stays_finite_and_consistent():
+    """3000 steps at full size (about 1.5 M episodes): no NaN/Inf, bookkeeping still closes, prefetch never misses."""
+    pkg = importlib.import_module(PKG)
+    a = _run(pkg, N, 3000, seed=7)
+    s = a["stats"]
+    assert s["episodes"] == a["dones"] == a["state"][:, 35].sum() > 10 * N
+    assert abs(s["env_steps"] + a["state"][:, 32].sum() - 3000 * N) < 0.5
+    assert s["inlane_resets"] <= 1e-4 * s["episodes"]             # episodes shorter than the 2-step prefetch pipeline are rare
+    assert np.isfinite(a["state"]).all()
+
+
+def test_inlane_fallback_is_used_when_episodes_are_shorter_than_the_prefetch_pipeline():
+    import torch
+    pkg = importlib.import_module(PKG)
+    env = pkg.Drone2dVecEnv(4096, seed=1, info_mode="none", mode="curriculum", scenario="stage_5", n_steps=1)
+    env.reset_device()
+    for _ in range(20):
+        env.step_device(None)
+    s = env.episode_stats()
+    assert s["episodes"] == 20 * 4096 and s["inlane_resets"] >= 18 * 4096
+    env.close()
