@@ -70,28 +70,38 @@ def build(force=False):
     return LIB_PATH
 
 
+def load(path):
+    """dlopen an oracle build and declare its prototypes (tests also load variant builds, e.g.
+    -DD2O_SPACE_DAMPING=0.9, to show that the genuine trajectories tell them apart)."""
+    L = C.CDLL(path)
+    L.d2o_default_config.argtypes = [C.POINTER(Config)]
+    L.d2o_moment_for_box.restype = C.c_double
+    L.d2o_moment_for_box.argtypes = [C.c_double] * 3
+    L.d2o_spawn.argtypes = [C.POINTER(State), C.c_double, C.c_double, C.c_double, C.POINTER(Config)]
+    L.d2o_space_step.restype = C.c_int
+    L.d2o_space_step.argtypes = [C.POINTER(State), C.POINTER(Obstacles), C.POINTER(Config), C.c_double, C.c_double]
+    L.d2o_path_eval.argtypes = [C.POINTER(Path), C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.d2o_path_gradient.argtypes = L.d2o_path_eval.argtypes
+    L.d2o_closest_u.restype = C.c_double
+    L.d2o_closest_u.argtypes = [C.POINTER(Path), C.c_double, C.c_double, C.POINTER(C.c_int), C.POINTER(C.c_double)]
+    L.d2o_observe.argtypes = [C.POINTER(State), C.POINTER(Path), C.POINTER(Obstacles), C.POINTER(Config), C.POINTER(StepOut)]
+    L.d2o_env_step.argtypes = [C.POINTER(State), C.POINTER(Path), C.POINTER(Obstacles), C.POINTER(Config),
+                               C.c_double, C.c_double, C.POINTER(StepOut)]
+    L.d2o_env_step_batch.argtypes = [C.c_int, C.POINTER(State), C.POINTER(Path), C.c_int, C.POINTER(Obstacles),
+                                     C.c_int, C.POINTER(Config), C.POINTER(C.c_float), C.POINTER(StepOut)]
+    L.d2o_philox4x32_10.argtypes = [C.POINTER(C.c_uint), C.POINTER(C.c_uint), C.POINTER(C.c_uint)]
+    L.d2o_after_physics.argtypes = [C.POINTER(State), C.POINTER(Path), C.POINTER(Obstacles), C.POINTER(Config),
+                                    C.POINTER(StepOut)]
+    L.d2o_frame_touches.restype = C.c_int
+    L.d2o_frame_touches.argtypes = [C.POINTER(Body), C.POINTER(Obstacles), C.POINTER(Config)]
+    return L
+
+
 def lib():
     global _lib
     if _lib is None:
         build()
-        L = C.CDLL(LIB_PATH)
-        L.d2o_default_config.argtypes = [C.POINTER(Config)]
-        L.d2o_moment_for_box.restype = C.c_double
-        L.d2o_moment_for_box.argtypes = [C.c_double] * 3
-        L.d2o_spawn.argtypes = [C.POINTER(State), C.c_double, C.c_double, C.c_double, C.POINTER(Config)]
-        L.d2o_space_step.restype = C.c_int
-        L.d2o_space_step.argtypes = [C.POINTER(State), C.POINTER(Obstacles), C.POINTER(Config), C.c_double, C.c_double]
-        L.d2o_path_eval.argtypes = [C.POINTER(Path), C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]
-        L.d2o_path_gradient.argtypes = L.d2o_path_eval.argtypes
-        L.d2o_closest_u.restype = C.c_double
-        L.d2o_closest_u.argtypes = [C.POINTER(Path), C.c_double, C.c_double, C.POINTER(C.c_int), C.POINTER(C.c_double)]
-        L.d2o_observe.argtypes = [C.POINTER(State), C.POINTER(Path), C.POINTER(Obstacles), C.POINTER(Config), C.POINTER(StepOut)]
-        L.d2o_env_step.argtypes = [C.POINTER(State), C.POINTER(Path), C.POINTER(Obstacles), C.POINTER(Config),
-                                   C.c_double, C.c_double, C.POINTER(StepOut)]
-        L.d2o_env_step_batch.argtypes = [C.c_int, C.POINTER(State), C.POINTER(Path), C.c_int, C.POINTER(Obstacles),
-                                         C.c_int, C.POINTER(Config), C.POINTER(C.c_float), C.POINTER(StepOut)]
-        L.d2o_philox4x32_10.argtypes = [C.POINTER(C.c_uint), C.POINTER(C.c_uint), C.POINTER(C.c_uint)]
-        _lib = L
+        _lib = load(LIB_PATH)
     return _lib
 
 
@@ -186,14 +196,14 @@ def env_step(state, path, obstacles, cfg, a_left, a_right):
     return out
 
 
-def env_step_batch(states, paths, obstacles, cfg, actions):
+def env_step_batch(states, paths, obstacles, cfg, actions, L=None):
     """states: (State * n); paths / obstacles: one struct (shared) or an array of n."""
     n = len(states)
     actions = np.ascontiguousarray(actions, dtype=np.float32).reshape(n, 2)
     outs = (StepOut * n)()
     p_arr = isinstance(paths, C.Array)
     o_arr = isinstance(obstacles, C.Array)
-    lib().d2o_env_step_batch(
+    (L or lib()).d2o_env_step_batch(
         n, states,
         paths if p_arr else C.pointer(paths), 1 if p_arr else 0,
         obstacles if o_arr else C.pointer(obstacles), 1 if o_arr else 0,

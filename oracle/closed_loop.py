@@ -28,13 +28,21 @@ def act(actor, obs, rng, deterministic=False):
     return np.clip(mu, -1, 1).astype(np.float32)
 
 
-def evaluate(mode, scenario, n_episodes, seed=0, deterministic=False, cfg_kwargs=None):
+def evaluate(mode, scenario, n_episodes, seed=0, deterministic=False, cfg_kwargs=None, cfg_overrides=None,
+             record_paths=False, lib_path=None):
+    """`cfg_overrides` sets raw d2o_config fields (e.g. iterations), `lib_path` runs the transitions on
+    another build of the oracle, `record_paths` adds the frame position after every step
+    (world coordinates) as res["flight_paths"]; all three serve tests/test_reference_trajectories_cpu.py."""
     random.seed(seed)
     np.random.seed(seed)
     rng = np.random.RandomState(seed + 77)
     actor = load_actor()
     kw = dict(cfg_kwargs or {})
     cfg = ref_port.config_from_kwargs(kw)
+    for k, v in (cfg_overrides or {}).items():
+        if not hasattr(cfg, k):
+            raise KeyError(k)
+        setattr(cfg, k, v)
     draws = ref_port.NumpyDraws()
     n = n_episodes
     states = (B.State * n)()
@@ -50,7 +58,8 @@ def evaluate(mode, scenario, n_episodes, seed=0, deterministic=False, cfg_kwargs
         if not shared:
             paths[i] = pth.to_struct()
             obsts[i] = B.make_obstacles(ob)
-    lib = B.lib()
+    lib = B.load(lib_path) if lib_path else B.lib()
+    flights = [[] for _ in range(n)]
     obs = np.zeros((n, 27))
     out0 = B.StepOut()
     for i in range(n):
@@ -61,10 +70,12 @@ def evaluate(mode, scenario, n_episodes, seed=0, deterministic=False, cfg_kwargs
     res = {k: np.zeros(n) for k in ("n_successful_runs", "n_failed_runs", "n_collisions", "APE", "env_steps", "total_reward")}
     for _ in range(cfg.n_steps):
         actions = act(actor, obs, rng, deterministic)
-        outs = B.env_step_batch(states, paths, obsts, cfg, actions)
+        outs = B.env_step_batch(states, paths, obsts, cfg, actions, L=lib)
         for i in range(n):
             o = outs[i]
             obs[i] = o.obs[:]
+            if record_paths and alive[i]:
+                flights[i].append((states[i].body[0].px, states[i].body[0].py))
             if alive[i] and o.done:
                 alive[i] = False
                 res["n_successful_runs"][i] = o.end_reached
@@ -75,4 +86,6 @@ def evaluate(mode, scenario, n_episodes, seed=0, deterministic=False, cfg_kwargs
                 res["total_reward"][i] = states[i].total_reward
         if not alive.any():
             break
+    if record_paths:
+        res["flight_paths"] = [np.array(f) for f in flights]
     return res

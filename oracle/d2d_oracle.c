@@ -23,6 +23,13 @@
 #define M_PI 3.14159265358979323846
 #endif
 
+/* pymunk Space.damping: never set by the reference (default 1.0).  env:376-380 assigns a plain Python
+ * attribute `body.damping = 0.9`, which Chipmunk never sees; tests/test_physics_pin.py checks this
+ * against genuine pymunk trajectories by rebuilding the oracle with -DD2O_SPACE_DAMPING=0.9. */
+#ifndef D2O_SPACE_DAMPING
+#define D2O_SPACE_DAMPING 1.0
+#endif
+
 /* ------------------------------------------------------------------------- */
 /* small helpers                                                             */
 /* ------------------------------------------------------------------------- */
@@ -148,6 +155,16 @@ static int box_touches_circle(const d2o_body *f, double rc, double rs, double hw
     return sqrt(ex * ex + ey * ey) <= r;
 }
 
+int d2o_frame_touches(const d2o_body *frame, const d2o_obstacles *ob, const d2o_config *c)
+{
+    int hit = 0;
+    double rc = cos(frame->a), rs = sin(frame->a);
+    double hw = c->width / 2, hh = (c->height / 2) / 2;   /* box size (width, height/2), Drone.py:16 */
+    for (int k = 0; k < ob->n; k++)
+        if (box_touches_circle(frame, rc, rs, hw, hh, ob->x[k], ob->y[k], ob->r[k])) hit = 1;
+    return hit;
+}
+
 int d2o_space_step(d2o_state *s, const d2o_obstacles *ob, const d2o_config *c,
                    double action_left, double action_right)
 {
@@ -193,10 +210,7 @@ int d2o_space_step(d2o_state *s, const d2o_obstacles *ob, const d2o_config *c,
     /* 2. collision detection at the new poses: only the frame box (type 1)
      * against obstacle circles (type 2) has a handler (env:17-19,190-191);
      * everything is a sensor so nothing is ever solved. */
-    int hit = 0;
-    double hw = c->width / 2, hh = (c->height / 2) / 2;   /* box size (width, height/2), Drone.py:16 */
-    for (int k = 0; k < ob->n; k++)
-        if (box_touches_circle(&B[0], rc[0], rs[0], hw, hh, ob->x[k], ob->y[k], ob->r[k])) hit = 1;
+    int hit = d2o_frame_touches(&B[0], ob, c);
     if (hit) s->collided = 1;
 
     /* 4. cpPivotJoint preStep for the 6 joints. */
@@ -230,7 +244,7 @@ int d2o_space_step(d2o_state *s, const d2o_obstacles *ob, const d2o_config *c,
     /* 5. cpBodyUpdateVelocity, damping = pow(1, dt) = 1 (env:376-380 sets a
      * plain Python attribute and has no physical effect). */
     {
-        double damping = pow(1.0, dt);
+        double damping = pow(D2O_SPACE_DAMPING, dt);
         double f_x[3] = { fx, 0, 0 }, f_y[3] = { fy, 0, 0 }, tt[3] = { tq, 0, 0 };
         for (int i = 0; i < 3; i++) {
             B[i].vx = B[i].vx * damping + (c->gravity_x + f_x[i] * t.minv[i]) * dt;
@@ -534,12 +548,21 @@ void d2o_env_step(d2o_state *s, const d2o_path *p, const d2o_obstacles *ob,
                   const d2o_config *c, double action_left, double action_right,
                   d2o_step_out *o)
 {
+    d2o_space_step(s, ob, c, action_left, action_right);
+    s->steps += 1;                                          /* env:407 */
+    d2o_after_physics(s, p, ob, c, o);
+}
+
+/* env:421-615: everything step() does after space.step(): observation, reward terms,
+ * termination flags and the episode accumulators, for the pose/velocity/collision flag/step
+ * count already in *s.  Split out so that tests can replay genuine reference trajectories
+ * (Tests/<scenario>/flight_paths) through the reward without the restated physics. */
+void d2o_after_physics(d2o_state *s, const d2o_path *p, const d2o_obstacles *ob,
+                       const d2o_config *c, d2o_step_out *o)
+{
     const double W = c->screen_x, H = c->screen_y;
     const double TWO_PI = 2 * M_PI;
     memset(o, 0, sizeof *o);
-
-    d2o_space_step(s, ob, c, action_left, action_right);
-    s->steps += 1;                                          /* env:407 */
     d2o_observe(s, p, ob, c, o);
     const double *obs = o->obs;
 

@@ -15,8 +15,14 @@
  *              cpSpaceStep / cpBodyUpdatePosition / cpBodyUpdateVelocity /
  *              cpPivotJoint algorithm for this world (3 bodies, 6 pivots,
  *              10 iterations) and is anchored only on the reference's call
- *              sites (Drone.py:9-95, drone_2d_env.py:184-191,403-406) and on
- *              closed-loop statistics (tests/golden/closed_loop.json).
+ *              sites (Drone.py:9-95, drone_2d_env.py:184-191,403-406), on
+ *              closed-loop statistics (tests/golden/closed_loop.json) and on the
+ *              genuine pymunk trajectories of the reference's evaluation runs
+ *              (tests/golden/reference_trajectories.npz: implied-thrust
+ *              distribution; tests/test_reference_trajectories_cpu.py).
+ *   pinned on genuine step() outputs (same fixtures): APE, termination step
+ *              and reason, total reward of 70 reference episodes replayed
+ *              through d2o_after_physics.
  */
 #ifndef D2D_ORACLE_H
 #define D2D_ORACLE_H
@@ -127,6 +133,15 @@ void d2o_observe(d2o_state *s, const d2o_path *p, const d2o_obstacles *ob,
 void d2o_env_step(d2o_state *s, const d2o_path *p, const d2o_obstacles *ob,
                   const d2o_config *c, double action_left, double action_right,
                   d2o_step_out *o);
+
+/* env:421-615: the part of step() after space.step() (observation, reward, termination,
+ * accumulators) on the state as it stands; d2o_env_step = d2o_space_step + steps++ + this. */
+void d2o_after_physics(d2o_state *s, const d2o_path *p, const d2o_obstacles *ob,
+                       const d2o_config *c, d2o_step_out *o);
+
+/* The begin-callback condition of env:17-19,190-191 at a given frame pose: 1 iff the frame box
+ * (width x height/2, Drone.py:16) touches any obstacle circle. */
+int d2o_frame_touches(const d2o_body *frame, const d2o_obstacles *ob, const d2o_config *c);
 
 /* Batch helpers (AoS arrays of n envs; path/obstacles either shared (stride 0)
  * or per env (stride 1)); actions float32 [n,2] like the gym boundary. */
