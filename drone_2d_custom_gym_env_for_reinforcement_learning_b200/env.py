@@ -9,7 +9,7 @@ from .vec_env import Drone2dVecEnv, INFO_KEYS
 
 
 class Drone2dEnv:
-    metadata = {"render_modes": []}
+    metadata = {"render_modes": ["rgb_array"]}
 
     def __init__(self, device=None, seed=0, **kwargs):
         self.kwargs = kwargs
@@ -18,12 +18,14 @@ class Drone2dEnv:
         self.action_space = self._vec.action_space
         self.done = False
         self.info = {}
+        self._flight_path = []
 
     def reset(self):
         """env:908-912: everything is re-initialised; returns the first observation."""
         self._vec.reset_device()
         self.done = False
         self.info = {k: 0 for k in INFO_KEYS}
+        self._flight_path = []
         return self._vec.obs64.cpu().numpy()[0].copy()
 
     def step(self, action):
@@ -36,12 +38,24 @@ class Drone2dEnv:
         info = self._vec._info_row(row, done)
         if info["dist_closest_obs"] == float("inf"):
             info["dist_closest_obs"] = np.inf
+        if self.kwargs.get("render_path", False):
+            # env:410-415,984-986: (x, screen_height - y) of the frame after every step, handed out at the end
+            W, H = self._vec.cfg.screen_x, self._vec.cfg.screen_y
+            self._flight_path.append(((obs[6] + 1.0) * W / 2.0, H - (obs[7] + 1.0) * H / 2.0))
+            if done:
+                info["flight_path"] = self._flight_path
         self.done = self.done or done
         self.info = info
         return obs, float(row[0]), self.done, info
 
     def render(self, mode="human", close=False):
-        return None
+        """env:775-776: nothing unless `render_sim` was requested.  With it, the frame the reference would
+        put on the pygame window is returned as an RGB array instead (render.py; no window is opened)."""
+        if not self.kwargs.get("render_sim", False):
+            return None
+        if self.kwargs.get("render_path", False):
+            return self._vec.render(flight_path=self._flight_path)
+        return self._vec.render()
 
     def close(self):
         self._vec.close()

@@ -96,7 +96,7 @@ class Drone2dVecEnv:
     N); "none" -> no per-env float64 taps at all (benchmarks).
     """
 
-    metadata = {"render_modes": []}
+    metadata = {"render_modes": ["rgb_array"]}
 
     def __init__(self, num_envs, device=None, seed=0, env_id_base=0, info_mode="episode", **kwargs):
         if not torch.cuda.is_available():
@@ -140,6 +140,8 @@ class Drone2dVecEnv:
         self._h_done = torch.zeros(n, dtype=torch.uint8).pin_memory()
         self._pending = None
         self._closed = False
+        self._renderer = None
+        self._last_actions = None
 
     # ------------------------------------------------------------------ helpers
     def _stream(self):
@@ -194,6 +196,7 @@ class Drone2dVecEnv:
                                     self.rewards.data_ptr(), self.dones.data_ptr(),
                                     self.terminal_obs.data_ptr() if terminal_obs else None,
                                     1 if auto_reset else 0, self._stream()))
+        self._last_actions = a
         return self.obs, self.rewards, self.dones
 
     # ------------------------------------------------------------- SB3 VecEnv API
@@ -289,11 +292,19 @@ class Drone2dVecEnv:
         idx = range(self.num_envs) if indices is None else ([indices] if isinstance(indices, int) else indices)
         return [False for _ in idx]
 
-    def render(self, mode="human"):
-        return None
+    def render(self, mode="rgb_array", index=0, pixels=None, flight_path=None):
+        """Renderer adapter (render.py): uint8 [h, w, 3] frame of env `index`, composed like the reference's
+        Drone2dEnv.render (env:775-906).  Copies that env's state to the host; not for use inside a hot loop."""
+        from .render import FrameRenderer
+        if self._renderer is None or self._renderer.pixels != pixels:
+            self._renderer = FrameRenderer(self, pixels=pixels)
+        act = None if self._last_actions is None else self._last_actions[index].cpu().numpy()
+        return self._renderer.frame(index, action=act, flight_path=flight_path)
 
-    def get_images(self):
-        return []
+    def get_images(self, indices=None, pixels=325):
+        """SB3 VecEnv.get_images: one frame per env (bounded to the first 16 unless `indices` is given)."""
+        idx = range(min(self.num_envs, 16)) if indices is None else indices
+        return [self.render(index=i, pixels=pixels) for i in idx]
 
     # ------------------------------------------------- state / tables / statistics
     def get_state(self):
