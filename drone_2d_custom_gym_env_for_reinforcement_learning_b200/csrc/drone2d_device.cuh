@@ -317,11 +317,29 @@ struct PathCursor {
     // the two polynomial rows live in a lane-private shared-memory column
     // (coef[r * D2D_BLOCK], r = 0..5 = a1, b1, c1, a2, b2, c2): 24 registers fewer during the
     // search, 6 conflict-free LDS.128 per evaluation instead.
-    double2 *coef;
+    // The column is addressed through a 32-bit shared-window address that is passed through a
+    // (no-op) warp shuffle: ptxas otherwise rematerialises &s_coef[tid] from S2R on every
+    // evaluation (S2R + S2UR + 4 integer ops on the critical path of each search iteration).
+    uint32_t caddr;
     double inv_seg;              // (N-1)/L: initial guess of the segment index (corrected exactly)
 
-    __device__ __forceinline__ PathCursor(const V &v_, double2 *coef_) : v(v_), N(v_.n_wps()), coef(coef_)
+    template <int R>
+    __device__ __forceinline__ double2 ld() const
     {
+        double2 r;
+        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2+%3];" : "=d"(r.x), "=d"(r.y) : "r"(caddr), "n"(R * D2D_BLOCK * 16));
+        return r;
+    }
+    template <int R>
+    __device__ __forceinline__ void st(double2 val)
+    {
+        asm volatile("st.shared.v2.f64 [%0+%1], {%2, %3};" ::"r"(caddr), "n"(R * D2D_BLOCK * 16), "d"(val.x), "d"(val.y) : "memory");
+    }
+
+    __device__ __forceinline__ PathCursor(const V &v_, double2 *coef_) : v(v_), N(v_.n_wps())
+    {
+        const uint32_t a = (uint32_t)__cvta_generic_to_shared(coef_);
+        caddr = __shfl_sync(__activemask(), a, threadIdx.x & 31);
         vlo_x = CUDART_INF; vhi_i = -CUDART_INF;                       // empty: the first use locates
         s_lo = CUDART_INF; s_hi = -CUDART_INF;
         lo = un1 = len = rlen = 0.0;
@@ -332,8 +350,8 @@ struct PathCursor {
 
     __device__ __forceinline__ void load_rows(int r1, int r2)
     {
-        coef[0] = v.pa(r1); coef[1 * D2D_BLOCK] = v.pb(r1); coef[2 * D2D_BLOCK] = v.pc(r1);
-        coef[3 * D2D_BLOCK] = v.pa(r2); coef[4 * D2D_BLOCK] = v.pb(r2); coef[5 * D2D_BLOCK] = v.pc(r2);
+        st<0>(v.pa(r1)); st<1>(v.pb(r1)); st<2>(v.pc(r1));
+        st<3>(v.pa(r2)); st<4>(v.pb(r2)); st<5>(v.pc(r2));
     }
 
     __device__ __forceinline__ void locate(double u)
@@ -379,10 +397,10 @@ struct PathCursor {
     {
         if (!hit(u)) locate(u);
         const double uu = S::mul(u, u);
-        const double2 a2 = coef[3 * D2D_BLOCK], b2 = coef[4 * D2D_BLOCK], c2 = coef[5 * D2D_BLOCK];
+        const double2 a2 = ld<3>(), b2 = ld<4>(), c2 = ld<5>();
         const double x2 = poly2(a2.x, b2.x, c2.x, u, uu), y2 = poly2(a2.y, b2.y, c2.y, u, uu);
         if (u >= s_lo && u <= s_hi) { x = x2; y = y2; return; }
-        const double2 a1 = coef[0], b1 = coef[1 * D2D_BLOCK], c1 = coef[2 * D2D_BLOCK];
+        const double2 a1 = ld<0>(), b1 = ld<1>(), c1 = ld<2>();
         const double mu_r = div_len(S::sub(u, lo));
         const double mu_f = div_len(S::sub(un1, u));
         const double x1 = poly2(a1.x, b1.x, c1.x, u, uu), y1 = poly2(a1.y, b1.y, c1.y, u, uu);
