@@ -126,6 +126,7 @@ __global__ void __launch_bounds__(D2D_BLOCK, D2D_MIN_BLOCKS) d2d_step_kernel(con
     __shared__ D2dSharedTables s_tab;
     __shared__ double s_us[PER_ENV ? D2D_MAX_WPS * D2D_BLOCK : 1];   // lane-private us[] columns
     __shared__ double2 s_coef[6 * D2D_BLOCK];                        // lane-private polynomial rows (PathCursor)
+    __shared__ int s_swap[PER_ENV ? D2D_BLOCK : 1];                  // >= 0: this lane consumed its prefetched episode (= its n_obs)
 
     const int tid = threadIdx.x;
     const D2dConst &c = p.c;
@@ -134,6 +135,7 @@ __global__ void __launch_bounds__(D2D_BLOCK, D2D_MIN_BLOCKS) d2d_step_kernel(con
     if (!PER_ENV) stage_shared_tables(p, &s_tab, tid, D2D_BLOCK);
     if (tid < D2D_STATS_DOUBLES) s_stats[tid] = 0.0;
     if (tid == 0) s_any_done = 0;
+    if (PER_ENV) s_swap[tid] = -1;
     if (blockIdx.x == 0 && tid == 0) { p.qcount[q_clear] = 0; p.qcount[3 + q_clear] = 0; }
     __syncthreads();
 
@@ -270,51 +272,16 @@ __global__ void __launch_bounds__(D2D_BLOCK, D2D_MIN_BLOCKS) d2d_step_kernel(con
                 double nx, ny, na;
                 int n_obs, new_flags;
                 if (sm.x == next_ep) {
-                    // swap in the prefetched episode: copy its tables from the staging buffer (1) into the
-                    // live buffer (0), take the spawn pose + first observation.  (Copying ~0.8 KB once per
-                    // episode keeps the per-step working set dense: with a per-env buffer flip, live and
-                    // staged rows of neighbouring envs share cache lines and the table traffic doubles.)
+                    // swap in the prefetched episode: its tables go from the staging buffer (1) into the
+                    // live buffer (0) (warp-cooperative copy at the end of the kernel), the spawn pose and
+                    // first observation are taken here.  (Copying ~0.8 KB once per episode keeps the
+                    // per-step working set dense: with a per-env buffer flip, live and staged rows of
+                    // neighbouring envs share cache lines and the table traffic doubles.)
                     const double2 xy = p.stg_xy[i];
                     nx = xy.x; ny = xy.y; na = p.stg_an[i].x;
                     n_obs = sm.y;
                     new_flags = D2D_F_INIT | (sm.z ? D2D_F_LATCHED : 0);
-                    if (PER_ENV) {
-                        const uint32_t np32 = (uint32_t)p.np, li = (uint32_t)i;
-                        // batches of 4 table rows: 20 independent loads in flight, then 20 stores
-                        for (int k0 = 0; k0 < c.n_wps; k0 += 4) {
-                            double u4[4];
-                            double2 w4[4], a4[4], b4[4], c4[4];
-#pragma unroll
-                            for (int j = 0; j < 4; j++) {
-                                const int k = min(k0 + j, c.n_wps - 1);
-                                const uint32_t o = (uint32_t)k * np32 + li;
-                                u4[j] = p.us[p.stg_off8 + o]; w4[j] = p.wps[p.stg_off16 + o];
-                                a4[j] = p.pa[p.stg_off16 + o]; b4[j] = p.pb[p.stg_off16 + o]; c4[j] = p.pc[p.stg_off16 + o];
-                            }
-#pragma unroll
-                            for (int j = 0; j < 4; j++) {
-                                const int k = k0 + j;
-                                if (k >= c.n_wps) break;
-                                const uint32_t o = (uint32_t)k * np32 + li;
-                                p.us[o] = u4[j]; p.wps[o] = w4[j]; p.pa[o] = a4[j]; p.pb[o] = b4[j]; p.pc[o] = c4[j];
-                            }
-                        }
-                        for (int k0 = 0; k0 < n_obs; k0 += 4) {
-                            double2 x4[4];
-                            double r4[4];
-#pragma unroll
-                            for (int j = 0; j < 4; j++) {
-                                const uint32_t o = (uint32_t)min(k0 + j, n_obs - 1) * np32 + li;
-                                x4[j] = p.obxy[p.stg_off16 + o]; r4[j] = p.obr[p.stg_off8 + o];
-                            }
-#pragma unroll
-                            for (int j = 0; j < 4; j++) {
-                                if (k0 + j >= n_obs) break;
-                                const uint32_t o = (uint32_t)(k0 + j) * np32 + li;
-                                p.obxy[o] = x4[j]; p.obr[o] = r4[j];
-                            }
-                        }
-                    }
+                    if (PER_ENV) s_swap[tid] = n_obs;                // tables are copied by the whole warp, below
                     const float *sob = p.stg_obs + i * D2D_OBS_DIM;
 #pragma unroll
                     for (int j = 0; j < D2D_OBS_DIM; j++) row[j] = sob[j];
@@ -346,6 +313,43 @@ __global__ void __launch_bounds__(D2D_BLOCK, D2D_MIN_BLOCKS) d2d_step_kernel(con
                 if (r == 1 || r == 2) continue;
                 atomicMax(&p.role_cycles[r], d[r]); atomicAdd(&p.role_cycles[8 + r], d[r]); atomicAdd(&p.role_cycles[16 + r], 1ull);
             }
+        }
+    }
+    if (PER_ENV) {
+        // Table copy of the envs that consumed their prefetched episode, by the whole warp: one element
+        // per lane and round, all loads of an env in flight together (a finished lane copying its ~60-100
+        // strided elements alone stretched the slowest warp of the launch by ~15k cycles).
+        const int my_nobs = s_swap[tid];
+        unsigned m = __ballot_sync(0xffffffffu, my_nobs >= 0);
+        const int lane = tid & 31;
+        const uint32_t np32 = (uint32_t)p.np;
+        while (m) {
+            const int src = __ffs(m) - 1;
+            m &= m - 1;
+            const uint32_t e = (uint32_t)(blk * D2D_BLOCK + (tid & ~31) + src);
+            const int nob = __shfl_sync(0xffffffffu, my_nobs, src);
+            const int n16 = 4 * c.n_wps;                           // wps, pa, pb, pc rows: element t = 4 * row + array
+            auto arr16 = [&](int a) -> double2 * { return a == 0 ? p.wps : (a == 1 ? p.pa : (a == 2 ? p.pb : p.pc)); };
+            double2 v16[2], vob;
+            double v8[2];
+#pragma unroll
+            for (int r = 0; r < 2; r++) {
+                const int t = lane + 32 * r;
+                if (t < n16) v16[r] = arr16(t & 3)[p.stg_off16 + (uint32_t)(t >> 2) * np32 + e];
+                const int u = t - c.n_wps;                         // 8-byte elements: us rows, then obstacle radii
+                if (t < c.n_wps) v8[r] = p.us[p.stg_off8 + (uint32_t)t * np32 + e];
+                else if (u < nob) v8[r] = p.obr[p.stg_off8 + (uint32_t)u * np32 + e];
+            }
+            if (lane < nob) vob = p.obxy[p.stg_off16 + (uint32_t)lane * np32 + e];
+#pragma unroll
+            for (int r = 0; r < 2; r++) {
+                const int t = lane + 32 * r;
+                if (t < n16) arr16(t & 3)[(uint32_t)(t >> 2) * np32 + e] = v16[r];
+                const int u = t - c.n_wps;
+                if (t < c.n_wps) p.us[(uint32_t)t * np32 + e] = v8[r];
+                else if (u < nob) p.obr[(uint32_t)u * np32 + e] = v8[r];
+            }
+            if (lane < nob) p.obxy[(uint32_t)lane * np32 + e] = vob;
         }
     }
     __syncthreads();
