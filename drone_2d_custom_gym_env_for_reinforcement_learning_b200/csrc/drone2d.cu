@@ -513,87 +513,7 @@ __global__ void d2d_gae_kernel(const float *__restrict__ rewards, const float *_
     }
 }
 
-// The shipped SB3 MlpPolicy actor (main.py:251,262 `PPO.load` / `model.predict`):
-// obs[27] -> tanh(W0 x + b0)[64] -> tanh(W1 h + b1)[64] -> W2 h + b2 = mean[2];
-// action = clip(mean + exp(log_std) * eps, -1, 1), eps ~ N(0,1) from the Philox stream keyed by
-// (seed, global env id, step) or eps = 0.  float32 like the reference's torch-CPU policy.  One lane
-// per environment, all weights (24 KB) in shared memory read as broadcast LDS.128; the second hidden
-// layer is consumed on the fly, so a lane holds only x[27] / h1[64] in registers.
-struct D2dPolicyWeights {
-    float w0[64 * 28];   // row j: 27 weights + bias
-    float w1[64 * 64];
-    float b1[64];
-    float w2[2 * 64];
-    float b2[2];
-    float std[2];
-};
-
-#define D2D_STREAM_POLICY 0x504F4C49u   // 'POLI'
-
-__global__ void __launch_bounds__(128) d2d_policy_kernel(const D2dPolicyWeights *__restrict__ wts, const float *__restrict__ obs,
-                                                          float *__restrict__ actions, int64_t n, int stochastic,
-                                                          uint32_t seed_lo, uint32_t seed_hi, int64_t env_id_base,
-                                                          uint64_t step_index)
-{
-    __shared__ __align__(16) D2dPolicyWeights w;
-    __shared__ float s_x[128 * 27];
-    const int tid = threadIdx.x;
-    {
-        const float4 *src = reinterpret_cast<const float4 *>(wts);
-        float4 *dst = reinterpret_cast<float4 *>(&w);
-        for (int k = tid; k < (int)(sizeof(D2dPolicyWeights) / 16); k += 128) dst[k] = src[k];
-    }
-    const int64_t base = (int64_t)blockIdx.x * 128;
-    const int rows = (int)min((int64_t)128, n - base);
-    for (int k = tid; k < rows * 27; k += 128) s_x[k] = obs[base * 27 + k];          // coalesced tile load
-    __syncthreads();
-    if (tid >= rows) return;
-    float x[27];
-#pragma unroll
-    for (int k = 0; k < 27; k++) x[k] = s_x[tid * 27 + k];
-    float h1[64];
-#pragma unroll
-    for (int j = 0; j < 64; j++) {
-        const float4 *r = reinterpret_cast<const float4 *>(&w.w0[j * 28]);
-        float acc = 0.0f;
-#pragma unroll
-        for (int q = 0; q < 7; q++) {
-            const float4 v = r[q];
-            acc = fmaf(v.x, x[4 * q], acc);
-            if (4 * q + 1 < 27) acc = fmaf(v.y, x[4 * q + 1], acc);
-            if (4 * q + 2 < 27) acc = fmaf(v.z, x[4 * q + 2], acc);
-            if (4 * q + 3 < 27) acc = fmaf(v.w, x[4 * q + 3], acc); else acc += v.w;   // slot 27 holds the bias
-        }
-        h1[j] = tanhf(acc);
-    }
-    float mu0 = w.b2[0], mu1 = w.b2[1];
-#pragma unroll 4
-    for (int j = 0; j < 64; j++) {
-        const float4 *r = reinterpret_cast<const float4 *>(&w.w1[j * 64]);
-        float acc = w.b1[j];
-#pragma unroll
-        for (int q = 0; q < 16; q++) {
-            const float4 v = r[q];
-            acc = fmaf(v.x, h1[4 * q], acc); acc = fmaf(v.y, h1[4 * q + 1], acc);
-            acc = fmaf(v.z, h1[4 * q + 2], acc); acc = fmaf(v.w, h1[4 * q + 3], acc);
-        }
-        const float h2 = tanhf(acc);
-        mu0 = fmaf(w.w2[j], h2, mu0);
-        mu1 = fmaf(w.w2[64 + j], h2, mu1);
-    }
-    if (stochastic) {
-        uint32_t o[4];
-        philox4x32_10((uint32_t)(env_id_base + base + tid), (uint32_t)step_index, (uint32_t)(step_index >> 32),
-                      D2D_STREAM_POLICY, seed_lo, seed_hi, o);
-        const double u1 = u01_from_bits(o[0], o[1]), u2 = u01_from_bits(o[2], o[3]);
-        const double rr = sqrt(-2.0 * log(1.0 - u1));
-        double sn, cs;
-        sincos(D2D_TWO_PI * u2, &sn, &cs);
-        mu0 += w.std[0] * (float)(rr * cs);
-        mu1 += w.std[1] * (float)(rr * sn);
-    }
-    reinterpret_cast<float2 *>(actions)[base + tid] = make_float2(fminf(fmaxf(mu0, -1.0f), 1.0f), fminf(fmaxf(mu1, -1.0f), 1.0f));
-}
+#include "drone2d_policy.cuh"   // the policy in the loop: tcgen05 (TMEM-accumulated tf32x3) MLP kernel
 
 // ===========================================================================
 // host side: handle + C ABI
@@ -626,6 +546,7 @@ struct d2d_env {
     double *stats_dev;
     uint64_t step_index;
     int64_t launches;
+    int policy_grid_cap;         // persistent grid size of the policy kernel (0 = not queried yet)
     // L2 residency control of the hot prefix of the state (see d2d_create)
     void *l2_base;
     size_t l2_bytes;
@@ -1106,19 +1027,29 @@ int d2d_debug_closest_u(d2d_env *e, const double *pos_dev, double *u_dev, int32_
     return D2D_OK;
 }
 
-int d2d_policy_weights_bytes(void) { return (int)sizeof(D2dPolicyWeights); }
+int d2d_policy_weights_bytes(void) { return (int)sizeof(D2dPolicyImage); }
 
 int d2d_policy_pack(const float *w0, const float *b0, const float *w1, const float *b1, const float *w2, const float *b2,
                     const float *log_std, void *packed_host)
 {
     if (!w0 || !b0 || !w1 || !b1 || !w2 || !b2 || !log_std || !packed_host) return fail(D2D_EINVAL, "NULL argument");
-    D2dPolicyWeights *p = (D2dPolicyWeights *)packed_host;
-    for (int j = 0; j < 64; j++) {
-        for (int k = 0; k < 27; k++) p->w0[j * 28 + k] = w0[j * 27 + k];
-        p->w0[j * 28 + 27] = b0[j];
+    D2dPolicyImage *p = (D2dPolicyImage *)packed_host;
+    memset(p, 0, sizeof *p);
+    for (int j = 0; j < D2D_POL_H; j++) {
+        for (int k = 0; k < D2D_POL_K0; k++) {           // 27 weights, the bias (matched by x[27] = 1), zero padding
+            const float v = k < 27 ? w0[j * 27 + k] : (k == 27 ? b0[j] : 0.0f);
+            const int o = d2d_umma_idx(j, k, D2D_POL_H);
+            p->w0_hi[o] = d2d_tf32_hi(v);
+            p->w0_lo[o] = v - p->w0_hi[o];
+        }
+        for (int k = 0; k < D2D_POL_K1; k++) {
+            const float v = w1[j * D2D_POL_K1 + k];
+            const int o = d2d_umma_idx(j, k, D2D_POL_H);
+            p->w1_hi[o] = d2d_tf32_hi(v);
+            p->w1_lo[o] = v - p->w1_hi[o];
+        }
         p->b1[j] = b1[j];
     }
-    memcpy(p->w1, w1, sizeof p->w1);
     memcpy(p->w2, w2, sizeof p->w2);
     p->b2[0] = b2[0]; p->b2[1] = b2[1];
     p->std[0] = expf(log_std[0]); p->std[1] = expf(log_std[1]);
@@ -1131,8 +1062,17 @@ int d2d_policy_act(d2d_env *e, const void *packed_weights_dev, const float *obs_
     if (!e || !packed_weights_dev || !obs_dev || !actions_dev) return fail(D2D_EINVAL, "NULL argument");
     DeviceGuard guard(e->device);
     const int64_t n = e->lay.n;
-    d2d_policy_kernel<<<grid_for(n, 128), 128, 0, (cudaStream_t)stream>>>(
-        (const D2dPolicyWeights *)packed_weights_dev, obs_dev, actions_dev, n, stochastic, e->p.c.seed_lo, e->p.c.seed_hi,
+    if (e->policy_grid_cap == 0) {
+        // persistent CTAs, two per SM (shared memory: 115.6 KB each; TMEM: 128 of 512 columns each)
+        CUDA_TRY(cudaFuncSetAttribute(d2d_policy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(D2dPolicySmem)));
+        int sms = 0;
+        CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, e->device));
+        e->policy_grid_cap = 2 * sms;
+    }
+    const int64_t tiles = (n + D2D_POL_TILE - 1) / D2D_POL_TILE;
+    const int grid = (int)(tiles < e->policy_grid_cap ? tiles : e->policy_grid_cap);
+    d2d_policy_kernel<<<grid, D2D_POL_THREADS, sizeof(D2dPolicySmem), (cudaStream_t)stream>>>(
+        (const D2dPolicyImage *)packed_weights_dev, obs_dev, actions_dev, n, stochastic, e->p.c.seed_lo, e->p.c.seed_hi,
         e->p.c.env_id_base, policy_step);
     e->launches++;
     CUDA_TRY(cudaGetLastError());

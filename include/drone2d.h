@@ -165,7 +165,10 @@ int d2d_debug_closest_u(d2d_env *env, const double *pos_dev, double *u_dev, int3
 /* Policy in the loop (the caller of step in the reference's test mode: `PPO.load` main.py:251,
  * `model.predict` main.py:262): the SB3 MlpPolicy actor 27 -> 64 -> 64 -> 2 (tanh) evaluated on
  * the device in ONE launch, so observations and actions never leave HBM/L2 between steps.
- *   d2d_policy_weights_bytes  size of the packed weight block
+ * The two hidden layers run on the tensor cores (tcgen05.mma kind::tf32, accumulators in TMEM,
+ * operands split hi + lo and three products accumulated, so the result agrees with a float32
+ * evaluation to ~3e-6); see csrc/drone2d_policy.cuh.
+ *   d2d_policy_weights_bytes  size of the packed weight block (an image of the kernel's shared memory)
  *   d2d_policy_pack           HOST: pack `policy.pth` tensors (row-major float32: w0 [64][27], b0 [64],
  *                             w1 [64][64], b1 [64], w2 [2][64], b2 [2], log_std [2]) into the block
  *   d2d_policy_act            actions[n][2] = clip(mean(obs) + std * eps, -1, 1); eps ~ N(0,1) from the
