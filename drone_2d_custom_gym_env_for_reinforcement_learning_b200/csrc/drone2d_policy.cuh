@@ -151,10 +151,12 @@ __device__ __forceinline__ float tanh_fast(float x)
 // layer 1: the two never live at the same time; its last KB also carries the partial outputs of the upper
 // column half between the last epilogue and the next tile's first), two mbarriers and the TMEM
 // base address.  115.5 KB -> two CTAs per SM.
+static_assert(sizeof(D2dPolicyImage) % 16 == 0, "bulk copies move multiples of 16 bytes");
+
 struct D2dPolicySmem {
     D2dPolicyImage w;
     float a[2 * D2D_POL_TILE * D2D_POL_K1];       // [hi | lo], each up to 128 x 64
-    unsigned long long bar[2];
+    unsigned long long bar[3];
     uint32_t tmem_base;
 };
 
@@ -178,7 +180,7 @@ __global__ void __launch_bounds__(D2D_POL_THREADS, 2) d2d_policy_kernel(const D2
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     D2dPolicySmem &S = *reinterpret_cast<D2dPolicySmem *>(smem_raw);
     const int tid = threadIdx.x, warp = tid >> 5, row = tid & (D2D_POL_TILE - 1), half = tid >> 7;
-    const uint32_t bar0 = pol::smem_u32(&S.bar[0]), bar1 = pol::smem_u32(&S.bar[1]);
+    const uint32_t bar0 = pol::smem_u32(&S.bar[0]), bar1 = pol::smem_u32(&S.bar[1]), barw = pol::smem_u32(&S.bar[2]);
     const int64_t n_tiles = (n + D2D_POL_TILE - 1) / D2D_POL_TILE;
 
     // the first tile's observations are requested before anything else, so that their latency overlaps the setup
@@ -189,34 +191,23 @@ __global__ void __launch_bounds__(D2D_POL_THREADS, 2) d2d_policy_kernel(const D2
     if (tid == 0) {
         pol::mbar_init(bar0, 1);
         pol::mbar_init(bar1, 1);
+        pol::mbar_init(barw, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        // the 49.9 KB weight image comes in as ONE bulk copy of the TMA unit, completing on barw
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(barw), "r"((uint32_t)sizeof(D2dPolicyImage)) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(pol::smem_u32(&S.w)),
+                     "l"(image), "r"((uint32_t)sizeof(D2dPolicyImage)), "r"(barw)
+                     : "memory");
     }
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(pol::smem_u32(&S.tmem_base)), "r"(128u)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    {
-        // 49.9 KB image: all of a thread's 13 loads are in flight before the first store (one L2 round trip)
-        constexpr int N16 = (int)(sizeof(D2dPolicyImage) / 16), PER = (N16 + D2D_POL_THREADS - 1) / D2D_POL_THREADS;
-        const float4 *src = reinterpret_cast<const float4 *>(image);
-        float4 *dst = reinterpret_cast<float4 *>(&S.w);
-        float4 buf[PER];
-#pragma unroll
-        for (int q = 0; q < PER; q++) {
-            const int k = tid + q * D2D_POL_THREADS;
-            if (k < N16) buf[q] = __ldg(&src[k]);
-        }
-#pragma unroll
-        for (int q = 0; q < PER; q++) {
-            const int k = tid + q * D2D_POL_THREADS;
-            if (k < N16) dst[k] = buf[q];
-        }
-    }
-    pol::async_proxy_fence();                    // weights were written through the generic proxy, the MMA reads them through the async proxy
     pol::tc_fence_before();
     __syncthreads();
     pol::tc_fence_after();
+    pol::mbar_wait(barw, 0);                     // the weight image has landed (async proxy -> async proxy: no proxy fence needed)
     const uint32_t tmem = S.tmem_base;
     const uint32_t tmem_lane = tmem + ((uint32_t)((warp & 3) * 32) << 16);   // a warp reaches the 32 TMEM lanes of its quarter
 
