@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(D2D_BLOCK, D2D_MIN_BLOCKS) d2d_step_kernel(con
                 stage_observe<PER_ENV>(p, &s_tab, (int64_t)qb[(int64_t)q_read * p.np + t],
                                        qb_tgt[(int64_t)q_read * p.np + t], &s_coef[tid]);
         }
-        if ((tid & 31) == 0 && first < (sample_role ? qa_cnt[q_read] : qb_cnt[q_read])) {
+        if (p.probe && (tid & 31) == 0 && first < (sample_role ? qa_cnt[q_read] : qb_cnt[q_read])) {
             const unsigned long long dt = (unsigned long long)(clock64() - t_start);
             const int r = sample_role ? 1 : 2;
             atomicMax(&p.role_cycles[r], dt); atomicAdd(&p.role_cycles[8 + r], dt); atomicAdd(&p.role_cycles[16 + r], 1ull);
@@ -303,7 +303,7 @@ __global__ void __launch_bounds__(D2D_BLOCK, D2D_MIN_BLOCKS) d2d_step_kernel(con
             }
         }
         store_scalars(p, i, s);
-        if ((tid & 31) == 0) {
+        if (p.probe && (tid & 31) == 0) {
             const long long t_end = clock64();
             const unsigned long long d[7] = {(unsigned long long)(t_end - t_start), 0, 0, (unsigned long long)(t_phys - t_start),
                                              (unsigned long long)(t_scan - t_phys), (unsigned long long)(t_obs - t_scan),
@@ -1124,6 +1124,7 @@ int d2d_debug_role_cycles(d2d_env *e, uint64_t *out24, int reset_after)
 {
     if (!e || !out24) return fail(D2D_EINVAL, "NULL argument");
     DeviceGuard guard(e->device);
+    e->p.probe = 1;                              // launches record their clock spans from the first call on
     CUDA_TRY(cudaDeviceSynchronize());
     CUDA_TRY(cudaMemcpy(out24, e->p.role_cycles, 24 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
     if (reset_after) CUDA_TRY(cudaMemset(e->p.role_cycles, 0, 24 * sizeof(uint64_t)));

@@ -205,7 +205,9 @@ int d2d_gae(const float *rewards_dev, const float *values_dev, const uint8_t *ep
  * [0] a main lane's whole step, [1] the episode-sampling refill role, [2] the first-observation
  * refill role, [3] thrust + rigid-body solve, [4] obstacle pass, [5] observation incl. the
  * closest-point search, [6] reward / termination / swap; [7] unused.
- * HOST uint64 [24], sync: out[r] = max, out[8 + r] = sum, out[16 + r] = number of warps. */
+ * HOST uint64 [24], sync: out[r] = max, out[8 + r] = sum, out[16 + r] = number of warps.
+ * Recording is off until the first call (which returns zeros) so that ordinary runs do not pay
+ * for the per-warp atomics. */
 int d2d_debug_role_cycles(d2d_env *env, uint64_t *out24, int reset_after);
 
 /* Number of kernels this library has launched on this handle. */
