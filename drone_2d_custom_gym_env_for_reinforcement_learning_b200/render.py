@@ -188,7 +188,7 @@ class FrameRenderer:
             path = PathTables(wps)
             self._path_cache[cache_key] = [tuple(path.point(u)) for u in np.linspace(0.0, path.length, self.path_samples)]
         state = env.get_state()[index]
-        obs = (env.obs64 if env.obs64 is not None else env.obs)[index].double().cpu().numpy()
+        obs = env.current_obs_row(index)
         rect = None
         if key == "shared" and env.kwargs.get("scenario") not in (None, "None"):
             # env:227-231: pygame.Rect(xmin, ymin, xmax - xmin, ymax) in SCREEN coordinates (not flipped, and the

@@ -98,7 +98,7 @@ class Drone2dVecEnv:
 
     metadata = {"render_modes": ["rgb_array"]}
 
-    def __init__(self, num_envs, device=None, seed=0, env_id_base=0, info_mode="episode", **kwargs):
+    def __init__(self, num_envs, device=None, seed=0, env_id_base=0, info_mode="episode", copy_outputs=True, **kwargs):
         if not torch.cuda.is_available():
             raise RuntimeError("Drone2dVecEnv needs a CUDA device: there is no CPU fallback")
         if info_mode not in ("episode", "full", "none"):
@@ -133,11 +133,20 @@ class Drone2dVecEnv:
             self.enable_taps()
         if self.cfg.mode == _lib.MODE_TEST:
             self.set_scenario(*scenario_tables(self.kwargs["scenario"], self.cfg.screen_x, self.cfg.screen_y))
-        # pinned host mirrors for the host-facing step()
+        # Page-locked host buffers of the host-facing step(): the kernel reads the actions from them and writes
+        # obs / reward / done / terminal observations into them directly (d2d_step_host_ex, mapped memory).
+        # Two output sets alternate, so the arrays of step t stay intact until step t + 2 (see copy_outputs).
+        self.copy_outputs = bool(copy_outputs)
         self._h_act = torch.zeros((n, 2), dtype=torch.float32).pin_memory()
-        self._h_obs = torch.zeros((n, 27), dtype=torch.float32).pin_memory()
-        self._h_rew = torch.zeros(n, dtype=torch.float32).pin_memory()
-        self._h_done = torch.zeros(n, dtype=torch.uint8).pin_memory()
+        self._h_out = [(torch.zeros((n, 27), dtype=torch.float32).pin_memory(), torch.zeros(n, dtype=torch.float32).pin_memory(),
+                        torch.zeros(n, dtype=torch.uint8).pin_memory()) for _ in range(2)]
+        self._h_term = torch.zeros((n, 27), dtype=torch.float32).pin_memory()
+        self._np_act = self._h_act.numpy()
+        self._np_out = [tuple(t.numpy() for t in trio) for trio in self._h_out]
+        self._np_term = self._h_term.numpy()
+        self._flip = 0
+        self._empty_infos = [_EMPTY_INFO] * n
+        self._host_stepped = False               # the newest observations are in the host buffers, not in self.obs
         self._pending = None
         self._closed = False
         self._renderer = None
@@ -197,6 +206,7 @@ class Drone2dVecEnv:
                                     self.terminal_obs.data_ptr() if terminal_obs else None,
                                     1 if auto_reset else 0, self._stream()))
         self._last_actions = a
+        self._host_stepped = False
         return self.obs, self.rewards, self.dones
 
     # ------------------------------------------------------------- SB3 VecEnv API
@@ -211,15 +221,17 @@ class Drone2dVecEnv:
         if self._pending is None:
             raise RuntimeError("step_wait() without step_async()")
         actions, self._pending = self._pending, None
-        self._h_act.copy_(torch.from_numpy(actions))
-        self.actions.copy_(self._h_act, non_blocking=True)
-        self.step_device(self.actions)
-        self._h_obs.copy_(self.obs, non_blocking=True)
-        self._h_rew.copy_(self.rewards, non_blocking=True)
-        self._h_done.copy_(self.dones, non_blocking=True)
-        torch.cuda.current_stream(self.device).synchronize()
-        dones = self._h_done.numpy().astype(bool)
-        return self._h_obs.numpy().copy(), self._h_rew.numpy().copy(), dones, self._build_infos(dones)
+        np.copyto(self._np_act, actions)
+        self._flip ^= 1
+        obs_t, rew_t, done_t = self._h_out[self._flip]
+        _lib.check(self._L.d2d_step_host_ex(self._h, self._h_act.data_ptr(), obs_t.data_ptr(), rew_t.data_ptr(), done_t.data_ptr(),
+                                            self._h_term.data_ptr(), 1, self._stream()))
+        self._host_stepped = True
+        obs, rew, done = self._np_out[self._flip]
+        dones = done.view(np.bool_)
+        if self.copy_outputs:
+            obs, rew, dones = obs.copy(), rew.copy(), dones.copy()
+        return obs, rew, dones, self._build_infos(dones)
 
     def step(self, actions):
         self.step_async(actions)
@@ -241,22 +253,21 @@ class Drone2dVecEnv:
 
     def _build_infos(self, dones):
         n = self.num_envs
+        idx = np.flatnonzero(dones)
         if self.info_mode == "full":
             rows = self.info.cpu().numpy()
             infos = [self._info_row(rows[i], dones[i]) for i in range(n)]
-            idx = np.flatnonzero(dones)
         else:
-            infos = [_EMPTY_INFO] * n
-            idx = np.flatnonzero(dones)
+            infos = list(self._empty_infos)
             if len(idx) and self.info is not None:
                 rows = self.info[torch.from_numpy(idx).to(self.device)].cpu().numpy()
                 for k, i in enumerate(idx):
                     infos[i] = self._info_row(rows[k], True)
-            elif len(idx):
+            else:
                 for i in idx:
                     infos[i] = {}
         if len(idx):
-            term = self.terminal_obs[torch.from_numpy(idx).to(self.device)].cpu().numpy()
+            term = self._np_term[idx]            # rows written by the kernel for the envs that finished in this step
             for k, i in enumerate(idx):
                 infos[i]["terminal_observation"] = term[k]
         return infos
@@ -298,8 +309,17 @@ class Drone2dVecEnv:
         from .render import FrameRenderer
         if self._renderer is None or self._renderer.pixels != pixels:
             self._renderer = FrameRenderer(self, pixels=pixels)
-        act = None if self._last_actions is None else self._last_actions[index].cpu().numpy()
+        if self._host_stepped:
+            act = self._np_act[index].copy()
+        else:
+            act = None if self._last_actions is None else self._last_actions[index].cpu().numpy()
         return self._renderer.frame(index, action=act, flight_path=flight_path)
+
+    def current_obs_row(self, index):
+        """float64 copy of env `index`'s newest observation, wherever the last step left it."""
+        if self._host_stepped:
+            return self._np_out[self._flip][0][index].astype(np.float64)
+        return (self.obs64 if self.obs64 is not None else self.obs)[index].double().cpu().numpy()
 
     def get_images(self, indices=None, pixels=325):
         """SB3 VecEnv.get_images: one frame per env (bounded to the first 16 unless `indices` is given)."""

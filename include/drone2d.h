@@ -120,11 +120,18 @@ int d2d_reset(d2d_env *env, const uint8_t *mask_dev, float *obs_dev, void *strea
 int d2d_step(d2d_env *env, const float *actions_dev, float *obs_dev, float *reward_dev,
              uint8_t *done_dev, float *terminal_obs_dev, int auto_reset, void *stream);
 
-/* Same transition through HOST buffers (the end-to-end boundary): copies the
- * actions host->device, launches the step, copies obs/reward/done back and
- * synchronises the stream.  Uses pinned staging buffers owned by the handle. */
+/* Same transition through HOST buffers (the end-to-end boundary), synchronous on `stream`.
+ * Page-locked caller buffers (cudaHostAlloc / cudaHostRegister / torch pin_memory) are mapped
+ * into the device's address space and used by the kernel directly: it reads the actions from
+ * them and writes obs/reward/done into them over PCIe, no staging copy.  Pageable buffers go
+ * through pinned staging buffers owned by the handle (H2D copy, launch, three D2H copies). */
 int d2d_step_host(d2d_env *env, const float *actions_host, float *obs_host, float *reward_host,
                   uint8_t *done_host, int auto_reset, void *stream);
+/* The same with the SB3 `terminal_observation` rows: terminal_obs_host (page-locked float32
+ * [n][27], or NULL) receives, for every env that finished in this step, the last observation of
+ * the finished episode; other rows are left untouched. */
+int d2d_step_host_ex(d2d_env *env, const float *actions_host, float *obs_host, float *reward_host,
+                     uint8_t *done_host, float *terminal_obs_host, int auto_reset, void *stream);
 
 /* Optional float64 taps of the LAST d2d_step/d2d_reset, for parity tests and the
  * info dict (env:575-613).  Pass device pointers (or NULL to disable):
