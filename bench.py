@@ -288,7 +288,7 @@ def run_ours(args):
             "clocks": clocks, "gpu_launches": launches,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": E * 2 * 4,
                     "d2h_bytes_per_step": E * (27 * 4 + 4 + 1), "steps": e2e_steps,
-                    "api": "d2d_step_host (C ABI, page-locked host buffers)"},
+                    "api": "d2d_step_host (C ABI; page-locked host buffers mapped into the step kernel: actions are read and obs/reward/done written over PCIe inside every step, then the stream is synchronised)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": E * ALGO_BYTES_STAGE5,
