@@ -132,6 +132,9 @@ __global__ void __launch_bounds__(D2D_BLOCK, D2D_MIN_BLOCKS) d2d_step_kernel(con
     const D2dConst &c = p.c;
     const int q_write = (int)(p.step_index % 3), q_read = (int)((p.step_index + 2) % 3), q_clear = (int)((p.step_index + 1) % 3);
 
+    // a dependent kernel launched with programmatic stream serialization (the policy kernel) may start its
+    // prologue while this grid runs; it synchronises on our completion before touching our outputs
+    asm volatile("griddepcontrol.launch_dependents;");
     if (!PER_ENV) stage_shared_tables(p, &s_tab, tid, D2D_BLOCK);
     if (tid < D2D_STATS_DOUBLES) s_stats[tid] = 0.0;
     if (tid == 0) s_any_done = 0;
@@ -1103,9 +1106,18 @@ int d2d_policy_act(d2d_env *e, const void *packed_weights_dev, const float *obs_
     }
     const int64_t tiles = (n + D2D_POL_TILE - 1) / D2D_POL_TILE;
     const int grid = (int)(tiles < e->policy_grid_cap ? tiles : e->policy_grid_cap);
-    d2d_policy_kernel<<<grid, D2D_POL_THREADS, sizeof(D2dPolicySmem), (cudaStream_t)stream>>>(
-        (const D2dPolicyImage *)packed_weights_dev, obs_dev, actions_dev, n, stochastic, e->p.c.seed_lo, e->p.c.seed_hi,
-        e->p.c.env_id_base, policy_step);
+    // programmatic dependent launch: the CTAs may become resident and set themselves up (barriers, TMEM, weight
+    // image) while the preceding step kernel drains; they read `obs` only after griddepcontrol.wait
+    cudaLaunchConfig_t lc;
+    memset(&lc, 0, sizeof lc);
+    lc.gridDim = dim3((unsigned)grid); lc.blockDim = dim3(D2D_POL_THREADS);
+    lc.dynamicSmemBytes = sizeof(D2dPolicySmem); lc.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    lc.attrs = attr; lc.numAttrs = 1;
+    CUDA_TRY(cudaLaunchKernelEx(&lc, d2d_policy_kernel, (const D2dPolicyImage *)packed_weights_dev, obs_dev, actions_dev, n, stochastic,
+                                e->p.c.seed_lo, e->p.c.seed_hi, e->p.c.env_id_base, (uint64_t)policy_step));
     e->launches++;
     CUDA_TRY(cudaGetLastError());
     return D2D_OK;

@@ -183,10 +183,6 @@ __global__ void __launch_bounds__(D2D_POL_THREADS, 2) d2d_policy_kernel(const D2
     const uint32_t bar0 = pol::smem_u32(&S.bar[0]), bar1 = pol::smem_u32(&S.bar[1]), barw = pol::smem_u32(&S.bar[2]);
     const int64_t n_tiles = (n + D2D_POL_TILE - 1) / D2D_POL_TILE;
 
-    // the first tile's observations are requested before anything else, so that their latency overlaps the setup
-    float xr[16];
-    d2d_policy_fetch(obs, n, (int64_t)blockIdx.x * D2D_POL_TILE + row, half, xr);
-
     // ---- one-time setup: barriers, TMEM (128 columns: layer-0 and layer-1 accumulators), weights ----
     if (tid == 0) {
         pol::mbar_init(bar0, 1);
@@ -204,6 +200,11 @@ __global__ void __launch_bounds__(D2D_POL_THREADS, 2) d2d_policy_kernel(const D2
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    // Programmatic dependent launch: everything above (barriers, TMEM, the weight image) may run while the
+    // step kernel that produces `obs` is still finishing; nothing below may.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    float xr[16];
+    d2d_policy_fetch(obs, n, (int64_t)blockIdx.x * D2D_POL_TILE + row, half, xr);
     pol::tc_fence_before();
     __syncthreads();
     pol::tc_fence_after();

@@ -133,3 +133,33 @@ def test_error_paths(pkg):
         env.set_stage(3)
     assert env._L.d2d_step(env._h, None, None, None, None, None, 1, None) == -1
     env.close()
+
+
+def test_host_step_zero_copy_views_alternate(pkg):
+    """copy_outputs=False: step() hands out views of two page-locked buffer sets that the kernel writes directly;
+    the arrays of step t survive step t + 1 and are reused by step t + 2.  Values equal the copying path."""
+    a = pkg.Drone2dVecEnv(512, seed=3, info_mode="none", copy_outputs=False, mode="curriculum", scenario="stage_3")
+    b = pkg.Drone2dVecEnv(512, seed=3, info_mode="none", mode="curriculum", scenario="stage_3")
+    a.reset(); b.reset()
+    rng = np.random.RandomState(1)
+    kept = []
+    for t in range(6):
+        act = rng.uniform(-1, 1, (512, 2)).astype(np.float32)
+        oa, ra, da, ia = a.step(act)
+        ob, rb, db, ib = b.step(act)
+        assert np.array_equal(oa, ob) and np.array_equal(ra, rb) and np.array_equal(da, db)
+        assert not oa.flags.owndata and ob.flags.owndata
+        kept.append((oa, ob.copy()))
+        if t >= 1:
+            assert np.array_equal(kept[t - 1][0], kept[t - 1][1])          # the previous step's view is still intact
+        if t >= 2:
+            assert np.shares_memory(kept[t - 2][0], oa) and not np.shares_memory(kept[t - 1][0], oa)
+    # terminal observations of finished envs arrive through the same mapped buffers
+    for _ in range(400):
+        act = rng.uniform(-1, 1, (512, 2)).astype(np.float32)
+        oa, ra, da, ia = a.step(act)
+        ob, rb, db, ib = b.step(act)
+        for i in np.flatnonzero(da):
+            assert np.array_equal(ia[i]["terminal_observation"], ib[i]["terminal_observation"])
+            assert not np.array_equal(ia[i]["terminal_observation"], oa[i])   # obs already belongs to the next episode
+    a.close(); b.close()
