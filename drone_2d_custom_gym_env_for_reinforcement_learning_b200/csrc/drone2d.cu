@@ -139,6 +139,7 @@ __global__ void __launch_bounds__(D2D_BLOCK, D2D_MIN_BLOCKS) d2d_step_kernel(con
     if (tid < D2D_STATS_DOUBLES) s_stats[tid] = 0.0;
     if (tid == 0) s_any_done = 0;
     if (PER_ENV) s_swap[tid] = -1;
+    asm volatile("griddepcontrol.wait;" ::: "memory");          // from here on the previous kernel's writes are visible
     if (blockIdx.x == 0 && tid == 0) { p.qcount[q_clear] = 0; p.qcount[3 + q_clear] = 0; }
     __syncthreads();
 
@@ -910,15 +911,21 @@ int d2d_step(d2d_env *e, const float *actions_dev, float *obs_dev, float *reward
     cudaLaunchConfig_t lc;
     memset(&lc, 0, sizeof lc);
     lc.gridDim = dim3((unsigned)grid); lc.blockDim = dim3(D2D_BLOCK); lc.dynamicSmemBytes = 0; lc.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
+    // Programmatic dependent launch: the blocks of this step may become resident while the previous kernel of
+    // the stream (the previous step, or the policy kernel) drains; they touch global memory only after
+    // griddepcontrol.wait.  The previous grid is fully resident or done by then, so nothing can starve.
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    lc.attrs = attr; lc.numAttrs = 1;
     if (e->l2_bytes) {
-        attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
-        attr[0].val.accessPolicyWindow.base_ptr = e->l2_base;
-        attr[0].val.accessPolicyWindow.num_bytes = e->l2_bytes;
-        attr[0].val.accessPolicyWindow.hitRatio = e->l2_hit_ratio;
-        attr[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-        attr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-        lc.attrs = attr; lc.numAttrs = 1;
+        attr[1].id = cudaLaunchAttributeAccessPolicyWindow;
+        attr[1].val.accessPolicyWindow.base_ptr = e->l2_base;
+        attr[1].val.accessPolicyWindow.num_bytes = e->l2_bytes;
+        attr[1].val.accessPolicyWindow.hitRatio = e->l2_hit_ratio;
+        attr[1].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        attr[1].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        lc.numAttrs = 2;
     }
     if (e->cfg.mode == D2D_MODE_CURRICULUM) CUDA_TRY(cudaLaunchKernelEx(&lc, d2d_step_kernel<true>, p));
     else CUDA_TRY(cudaLaunchKernelEx(&lc, d2d_step_kernel<false>, p));

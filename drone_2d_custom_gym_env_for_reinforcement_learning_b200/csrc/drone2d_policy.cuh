@@ -183,6 +183,7 @@ __global__ void __launch_bounds__(D2D_POL_THREADS, 2) d2d_policy_kernel(const D2
     const uint32_t bar0 = pol::smem_u32(&S.bar[0]), bar1 = pol::smem_u32(&S.bar[1]), barw = pol::smem_u32(&S.bar[2]);
     const int64_t n_tiles = (n + D2D_POL_TILE - 1) / D2D_POL_TILE;
 
+    asm volatile("griddepcontrol.launch_dependents;");           // the next step kernel may queue up behind us
     // ---- one-time setup: barriers, TMEM (128 columns: layer-0 and layer-1 accumulators), weights ----
     if (tid == 0) {
         pol::mbar_init(bar0, 1);
