@@ -170,7 +170,9 @@ def run_reference(args):
     budget = float(os.environ.get("D2D_CPU_BUDGET_S", "20"))
     cb = cpu_baseline_sample(budget)
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
-            "steps": steps, "warmup": warm, "ms_per_step": 1000.0 / cb["value"], "higher_is_better": True,
+            "steps": steps, "warmup": warm,
+            # same meaning as in our arm: the time one pass over one batch of envs_per_gpu environments takes
+            "ms_per_step": 1000.0 * args.envs_per_gpu / cb["value"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "envs_per_gpu": args.envs_per_gpu},
             "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
