@@ -23,7 +23,7 @@ EXPORTS = [
     "d2d_set_scenario", "d2d_set_tables", "d2d_get_tables", "d2d_reset", "d2d_step", "d2d_step_host",
     "d2d_step_host_ex",
     "d2d_set_taps", "d2d_get_state", "d2d_set_state", "d2d_episode_stats", "d2d_episode_stats_dev",
-    "d2d_debug_closest_u", "d2d_debug_role_cycles", "d2d_launch_count", "d2d_set_stage", "d2d_gae",
+    "d2d_debug_closest_u", "d2d_debug_role_cycles", "d2d_debug_skip_physics", "d2d_launch_count", "d2d_set_stage", "d2d_gae",
     "d2d_policy_weights_bytes", "d2d_policy_pack", "d2d_policy_act", "d2d_rollout",
 ]
 
@@ -83,6 +83,7 @@ def load():
     L.d2d_episode_stats_dev.argtypes = [vp, C.POINTER(vp)]
     L.d2d_debug_closest_u.argtypes = [vp, vp, vp, vp, vp]
     L.d2d_debug_role_cycles.argtypes = [vp, C.POINTER(C.c_uint64), i32]
+    L.d2d_debug_skip_physics.argtypes = [vp, i32]
     L.d2d_set_stage.argtypes = [vp, i32, C.c_double]
     L.d2d_gae.argtypes = [vp, vp, vp, vp, vp, i32, i64, C.c_float, C.c_float, vp, vp, vp]
     L.d2d_policy_pack.argtypes = [vp] * 8

@@ -207,7 +207,13 @@ __global__ void __launch_bounds__(D2D_BLOCK, D2D_MIN_BLOCKS) d2d_step_kernel(con
         }
 
         double rc0, rs0;
-        physics_step(s, c, (double)act.x, (double)act.y, rc0, rs0);
+        if (!p.skip_physics) {
+            physics_step(s, c, (double)act.x, (double)act.y, rc0, rs0);
+        } else {
+            // replay mode (tests): the injected state already is the outcome of space.step
+            const double2 sc = sincos2(s.an[0]);
+            rs0 = sc.x; rc0 = sc.y;
+        }
         s.steps += 1;                                               // env:407
         store_bodies(p, i, s);
         const long long t_phys = clock64();
@@ -1166,6 +1172,13 @@ int d2d_gae(const float *rewards_dev, const float *values_dev, const uint8_t *ep
         rewards_dev, values_dev, episode_starts_dev, last_values_dev, last_dones_dev, n_steps, n_envs, gamma, gae_lambda,
         advantages_dev, returns_dev);
     CUDA_TRY(cudaGetLastError());
+    return D2D_OK;
+}
+
+int d2d_debug_skip_physics(d2d_env *e, int enable)
+{
+    if (!e) return fail(D2D_EINVAL, "handle is NULL");
+    e->p.skip_physics = enable ? 1 : 0;
     return D2D_OK;
 }
 

@@ -179,6 +179,7 @@ struct D2dParams {
     const uint8_t *mask;
     double *obs64, *info, *stats;
     unsigned long long *role_cycles;   // [8] max clock64 span per role/phase of the last launches (profiling hook)
+    int skip_physics;                  // debug: take the pose/velocity in the state as the result of space.step (d2d_debug_skip_physics)
     int probe;                         // record role_cycles (off until d2d_debug_role_cycles is first called)
     uint64_t step_index;       // global step counter (keys the random-action stream)
     int auto_reset;

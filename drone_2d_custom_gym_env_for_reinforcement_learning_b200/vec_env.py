@@ -394,6 +394,10 @@ class Drone2dVecEnv:
         _lib.check(self._L.d2d_set_stage(self._h, int(stage), float(spawn_chance)))
         self.cfg.stage, self.cfg.stage_spawn_chance = int(stage), float(spawn_chance)
 
+    def debug_skip_physics(self, enable=True):
+        """Replay mode (d2d_debug_skip_physics): step() runs everything after space.step on the injected state."""
+        _lib.check(self._L.d2d_debug_skip_physics(self._h, 1 if enable else 0))
+
     def role_cycles(self, reset=True):
         """Profiling hook (d2d_debug_role_cycles): longest per-warp clock span per role / phase."""
         out = (C.c_uint64 * 24)()

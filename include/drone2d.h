@@ -217,6 +217,12 @@ int d2d_gae(const float *rewards_dev, const float *values_dev, const uint8_t *ep
  * for the per-warp atomics. */
 int d2d_debug_role_cycles(d2d_env *env, uint64_t *out24, int reset_after);
 
+/* Replay mode for tests: with enable != 0 the step kernel skips thrust + cpSpaceStep and treats the
+ * frame pose / velocity found in the state (d2d_set_state) as the outcome of space.step, i.e. it runs
+ * env:407-615 only.  tests/test_gpu_reference_trajectories.py pushes the reference's genuine pymunk
+ * trajectories through it and compares reward, APE and termination with what the reference wrote. */
+int d2d_debug_skip_physics(d2d_env *env, int enable);
+
 /* Number of kernels this library has launched on this handle. */
 int64_t d2d_launch_count(const d2d_env *env);
 

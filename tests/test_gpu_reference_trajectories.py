@@ -71,3 +71,67 @@ def test_implied_thrust_of_the_gpu_closed_loop_matches_genuine_pymunk():
     assert abs(s["frac_above_2000"] - ref["frac_above_2000"]) < 0.004
     assert abs(s["frac_below_5"] - ref["frac_below_5"]) < 0.003
     assert abs(s["horizontal_drag_coefficient"]) < 0.01
+
+
+@pytest.mark.parametrize("scenario", SCENARIOS)
+def test_gpu_replay_of_genuine_episodes_reproduces_reward_ape_and_termination(scenario):
+    """The product path itself on genuine data: the step kernel in replay mode (d2d_debug_skip_physics: everything
+    after space.step) is fed the reference's recorded positions, their first differences as velocity and the
+    thrust-direction angle estimate, exactly like oracle/flight_replay.py does for the oracle.  Per episode it must
+    give the APE the reference wrote (1e-9), end on the reference's last step for the same reason, and sum up the
+    reference's total reward (same bound as the CPU test); it must also agree with the oracle's replay of the same
+    inputs to rounding.  Episodes in which the angle estimate makes the frame box touch at the wrong step (the
+    oracle's own collision test decides which) are skipped: the kernel would, rightly, end them elsewhere."""
+    import torch
+    from oracle import binding as B
+    from oracle import flight_replay as FR
+    pkg = importlib.import_module(PKG)
+    z = np.load(os.path.join(GOLDEN, "reference_trajectories.npz"))
+    run_cfg = json.load(open(os.path.join(GOLDEN, "reference_trajectory_stats.json")))["run_config"]
+    lens = z[scenario + "__len"]
+    xy_all, off, eps = z[scenario + "__xy"], 0, []
+    ocfg = B.default_config(**run_cfg)
+    for k, n in enumerate(lens):
+        xy = xy_all[off:off + n]
+        off += n
+        ang = FR.estimate_angle(xy)
+        col = int(z[scenario + "__collision"][k])
+        ref = FR.replay_rewards(scenario, xy, col, cfg=ocfg, angles=ang)
+        if ref["touch"][:-1].any() or bool(ref["touch"][-1]) != bool(col):
+            continue
+        vel = np.empty_like(xy)
+        vel[:-1] = (xy[1:] - xy[:-1]) * 60.0
+        vel[-1] = 2 * vel[-2] - vel[-3]
+        eps.append(dict(xy=xy, vel=vel, ang=ang, col=col, total=float(z[scenario + "__total_reward"][k]),
+                        ape=float(z[scenario + "__ape"][k]), oracle=ref))
+    assert len(eps) >= 6, "too few usable episodes in the fixture"
+    n = len(eps)
+    env = pkg.Drone2dVecEnv(n, seed=0, info_mode="full", mode="test", scenario=scenario, **run_cfg)
+    env.reset_device()
+    env.debug_skip_physics(True)
+    zero = torch.zeros((n, 2), device=env.device)
+    st = env.get_state()
+    st[:, 18:36] = 0.0                                       # impulses, flags, counters, accumulators: a fresh episode
+    st[:, 31] = 0.0
+    total, ape, done_at, bits = np.zeros(n), np.zeros(n), [None] * n, [0] * n
+    for t in range(max(len(e["xy"]) for e in eps)):
+        for i, e in enumerate(eps):
+            if t < len(e["xy"]):
+                st[i, 0:6] = (e["xy"][t, 0], e["xy"][t, 1], e["vel"][t, 0], e["vel"][t, 1], e["ang"][t], 0.0)
+        env.set_state(st)
+        env.step_device(zero, auto_reset=False, terminal_obs=False)
+        info = env.info.cpu().numpy()
+        st = env.get_state()
+        for i, e in enumerate(eps):
+            if t < len(e["xy"]):
+                total[i], ape[i] = info[i, 10], info[i, 9]
+                if info[i, 11] != 0 and done_at[i] is None:
+                    done_at[i], bits[i] = t + 1, int(info[i, 11])
+    env.close()
+    for i, e in enumerate(eps):
+        T = len(e["xy"])
+        assert done_at[i] == T, (scenario, i, done_at[i], T)
+        assert bool(bits[i] & 1) == bool(e["col"])
+        assert abs(ape[i] - e["ape"]) < 1e-9, (ape[i], e["ape"])
+        assert abs(total[i] - e["total"]) < 6.0, (total[i], e["total"])
+        assert abs(total[i] - e["oracle"]["total_reward"]) < 1e-6 * T + 1e-4, (total[i], e["oracle"]["total_reward"])
