@@ -22,7 +22,7 @@ EXPORTS = [
     "d2d_abi_version", "d2d_last_error", "d2d_default_config", "d2d_state_bytes", "d2d_create", "d2d_destroy",
     "d2d_set_scenario", "d2d_set_tables", "d2d_get_tables", "d2d_reset", "d2d_step", "d2d_step_host",
     "d2d_step_host_ex",
-    "d2d_set_taps", "d2d_get_state", "d2d_set_state", "d2d_episode_stats", "d2d_episode_stats_dev",
+    "d2d_set_taps", "d2d_set_info_done_only", "d2d_get_state", "d2d_set_state", "d2d_episode_stats", "d2d_episode_stats_dev",
     "d2d_debug_closest_u", "d2d_debug_role_cycles", "d2d_debug_skip_physics", "d2d_launch_count", "d2d_set_stage", "d2d_gae",
     "d2d_policy_weights_bytes", "d2d_policy_pack", "d2d_policy_act", "d2d_rollout",
 ]
@@ -77,6 +77,7 @@ def load():
     L.d2d_step_host.argtypes = [vp, vp, vp, vp, vp, i32, vp]
     L.d2d_step_host_ex.argtypes = [vp, vp, vp, vp, vp, vp, i32, vp]
     L.d2d_set_taps.argtypes = [vp, vp, vp]
+    L.d2d_set_info_done_only.argtypes = [vp, i32]
     L.d2d_get_state.argtypes = [vp, dp]
     L.d2d_set_state.argtypes = [vp, dp]
     L.d2d_episode_stats.argtypes = [vp, dp, i32]

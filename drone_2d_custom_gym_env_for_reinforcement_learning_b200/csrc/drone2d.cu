@@ -240,7 +240,7 @@ __global__ void __launch_bounds__(D2D_BLOCK, D2D_MIN_BLOCKS) d2d_step_kernel(con
         reward_and_done(c, s, ax, v.n_obs() > 0, r);
         p.reward[i] = (float)r.reward;
         p.done[i] = r.done ? 1 : 0;
-        if (p.info) {
+        if (p.info && (r.done || !p.info_done_only)) {
             double *f = p.info + i * D2D_INFO_DOUBLES;
             f[0] = r.reward; f[1] = r.r_CA; f[2] = r.r_PA; f[3] = r.r_PP; f[4] = r.r_coll; f[5] = r.r_end;
             f[6] = r.r_AA; f[7] = (double)s.steps; f[8] = r.d1; f[9] = r.ape; f[10] = s.total_reward;
@@ -1172,6 +1172,13 @@ int d2d_gae(const float *rewards_dev, const float *values_dev, const uint8_t *ep
         rewards_dev, values_dev, episode_starts_dev, last_values_dev, last_dones_dev, n_steps, n_envs, gamma, gae_lambda,
         advantages_dev, returns_dev);
     CUDA_TRY(cudaGetLastError());
+    return D2D_OK;
+}
+
+int d2d_set_info_done_only(d2d_env *e, int enable)
+{
+    if (!e) return fail(D2D_EINVAL, "handle is NULL");
+    e->p.info_done_only = enable ? 1 : 0;
     return D2D_OK;
 }
 

@@ -179,6 +179,7 @@ struct D2dParams {
     const uint8_t *mask;
     double *obs64, *info, *stats;
     unsigned long long *role_cycles;   // [8] max clock64 span per role/phase of the last launches (profiling hook)
+    int info_done_only;                // write an env's info row only on the step that ends its episode (d2d_set_info_done_only)
     int skip_physics;                  // debug: take the pose/velocity in the state as the result of space.step (d2d_debug_skip_physics)
     int probe;                         // record role_cycles (off until d2d_debug_role_cycles is first called)
     uint64_t step_index;       // global step counter (keys the random-action stream)

@@ -143,6 +143,9 @@ int d2d_step_host_ex(d2d_env *env, const float *actions_host, float *obs_host, f
  *              u* (closest path parameter), Brent evaluations, nearest-obstacle
  *              indices packed (i0 + 256*i1 + 65536*i2, 255 = none), episode number */
 int d2d_set_taps(d2d_env *env, double *obs64_dev, double *info_dev);
+/* With enable != 0 the info tap receives an env's row only on the step that ends its episode (the
+ * rows SB3 reads: infos of finished envs); 0 (default): every env, every step. */
+int d2d_set_info_done_only(d2d_env *env, int enable);
 
 /* State blob (HOST, float64 [n][D2D_STATE_DOUBLES], sync): per env
  *   [0..17]  frame, left motor, right motor: px, py, vx, vy, angle, omega

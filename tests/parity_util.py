@@ -78,7 +78,7 @@ def oracle_config_from(env):
 def run_parity(pkg, mode, scenario, n_envs, n_rounds, seed=0, action_scale=1.0, inject_spawn=None, **kwargs):
     """Step `n_envs` environments for `n_steps` on the GPU and in the oracle; returns error statistics."""
     import torch
-    env = pkg.Drone2dVecEnv(n_envs, seed=seed, info_mode="episode", mode=mode, scenario=scenario, **kwargs)
+    env = pkg.Drone2dVecEnv(n_envs, seed=seed, info_mode="full", mode=mode, scenario=scenario, **kwargs)
     cfg = oracle_config_from(env)
     per_env = (mode == "curriculum")
     env.reset_device()

@@ -4,7 +4,7 @@ import numpy as np, torch
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, REPO)
 pkg = importlib.import_module("drone_2d_custom_gym_env_for_reinforcement_learning_b200")
 E = 65536
-env = pkg.Drone2dVecEnv(E, seed=0, info_mode="episode", mode="curriculum", scenario="stage_5")
+env = pkg.Drone2dVecEnv(E, seed=0, info_mode="full", mode="curriculum", scenario="stage_5")
 env.reset_device()
 g = torch.Generator(device=env.device); g.manual_seed(1)
 ring = (torch.rand((256, E, 2), device=env.device, generator=g) * 2 - 1).contiguous()
