@@ -54,9 +54,19 @@ def _profiled_traffic(envs):
             j = json.load(fh)
         if int(j.get("envs_per_launch", -1)) != int(envs):
             return None, None
+        _profiled_traffic.limiter = {
+            "note": "what actually bounds the kernel (same ncu capture): float64 latency/issue, not HBM",
+            "fp64_pipe_active_pct": j["launch"].get("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"),
+            "issue_slots_active_pct": j["launch"].get("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+            "warps_active_pct_of_max": j["launch"].get("sm__warps_active.avg.pct_of_peak_sustained_active"),
+            "active_lanes_per_warp_instruction": j["launch"].get("smsp__thread_inst_executed_per_inst_executed.ratio"),
+        }
         return float(j["dram_bytes_per_launch"]), os.path.basename(best)
     except Exception:  # noqa: BLE001
         return None, None
+
+
+_profiled_traffic.limiter = None
 
 
 def _peaks():
@@ -109,6 +119,29 @@ def _dist_env():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     return rank, world, local
+
+
+def bind_to_gpu_numa_node(local):
+    """One process per GPU: run on (and first-touch the page-locked buffers from) the CPU cores NVML reports as
+    local to this rank's GPU, so that the host end of the PCIe traffic stays on the GPU's NUMA node.  Best effort:
+    returns the number of cores bound to, or 0 if NVML / the affinity call is unavailable."""
+    try:
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        pr = torch.cuda.get_device_properties(local)
+        bus = "%08x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        h = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * w + b for w in range(words) for b in range(64) if (mask[w] >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if not cpus:
+            return 0
+        os.sched_setaffinity(0, cpus)
+        return len(cpus)
+    except Exception:  # noqa: BLE001
+        return 0
 
 
 def cpu_baseline_sample(budget_s, scenario="stage_5", mode="curriculum", workers=None):
@@ -189,6 +222,7 @@ def run_ours(args):
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback for the product path)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa_cores = bind_to_gpu_numa_node(local) if world > 1 else 0
     dist = None
     if world > 1:
         import torch.distributed as dist_mod
@@ -284,7 +318,7 @@ def run_ours(args):
             "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "envs_per_gpu": E, "l2_note": "state+tables per GPU = %.0f MB > L2 "
-                       "(126 MB): inputs larger than L2, no flush" % state_mb, "parallelism": "env-sharded x%d" % world,
+                       "(126 MB): inputs larger than L2, no flush" % state_mb, "parallelism": "env-sharded x%d" % world, "host_cores_bound_per_rank": numa_cores,
                        "actions": "device-resident ring of %d random batches" % R,
                        "steady_state_presteps": settle},
             "clocks": clocks, "gpu_launches": launches,
@@ -295,7 +329,8 @@ def run_ours(args):
                          "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": E * ALGO_BYTES_STAGE5,
                          "algorithmic_bytes_per_env_step": ALGO_BYTES_STAGE5,
-                         "kernel": "d2d_step_kernel<true>", "kernel_ms": per_launch_ms},
+                         "kernel": "d2d_step_kernel<true>", "kernel_ms": per_launch_ms,
+                         "limiter": _profiled_traffic.limiter},
             "episodes_finished": stats["episodes"],
         }
         if args.cpu_baseline:
