@@ -172,8 +172,6 @@ def cpu_baseline_sample(budget_s, scenario="stage_5", mode="curriculum", workers
 def _cpu_worker(w, budget_s, mode, scenario, q):
     import random
     import numpy as np
-    import contextlib
-    import io
     from oracle import ref_port
     random.seed(1000 + w)
     np.random.seed(1000 + w)

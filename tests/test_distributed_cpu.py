@@ -4,7 +4,6 @@ import importlib
 import os
 import socket
 
-import numpy as np
 import torch
 import torch.multiprocessing as mp
 

@@ -1,5 +1,5 @@
 """BASELINE config 4: `large` scenario, agent_19 policy driving 65536 envs end to end on the device."""
-import importlib, json, os, sys, time
+import importlib, json, os, sys
 import torch
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, REPO)
 PKG = "drone_2d_custom_gym_env_for_reinforcement_learning_b200"

@@ -1,6 +1,5 @@
 """agent_19 on all 12 settings, 4096 GPU episodes each, next to the reference's fixtures -> profiles/<tag>_closed_loop.md"""
 import importlib, json, os, sys
-import numpy as np
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, REPO)
 PKG = "drone_2d_custom_gym_env_for_reinforcement_learning_b200"
 pkg = importlib.import_module(PKG); policy = importlib.import_module(PKG + ".policy")

@@ -14,7 +14,6 @@ import json
 import os
 import shutil
 import subprocess
-import sys
 from collections import defaultdict
 
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

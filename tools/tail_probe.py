@@ -1,5 +1,5 @@
 """Per-launch critical-path probe: which role's slowest warp bounds each step kernel?"""
-import importlib, os, sys, json
+import importlib, os, sys
 import numpy as np, torch
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, REPO)
 pkg = importlib.import_module("drone_2d_custom_gym_env_for_reinforcement_learning_b200")
