@@ -914,8 +914,7 @@ int d2d_step(d2d_env *e, const float *actions_dev, float *obs_dev, float *reward
     p.terminal_obs = terminal_obs_dev; p.auto_reset = auto_reset; p.step_index = e->step_index++;
     cudaStream_t st = (cudaStream_t)stream;
     const int grid = grid_for(p.n, D2D_BLOCK) + 2 * p.refill_blocks;
-    cudaLaunchConfig_t lc;
-    memset(&lc, 0, sizeof lc);
+    cudaLaunchConfig_t lc = {};
     lc.gridDim = dim3((unsigned)grid); lc.blockDim = dim3(D2D_BLOCK); lc.dynamicSmemBytes = 0; lc.stream = st;
     cudaLaunchAttribute attr[2];
     // Programmatic dependent launch: the blocks of this step may become resident while the previous kernel of
@@ -1121,8 +1120,7 @@ int d2d_policy_act(d2d_env *e, const void *packed_weights_dev, const float *obs_
     const int grid = (int)(tiles < e->policy_grid_cap ? tiles : e->policy_grid_cap);
     // programmatic dependent launch: the CTAs may become resident and set themselves up (barriers, TMEM, weight
     // image) while the preceding step kernel drains; they read `obs` only after griddepcontrol.wait
-    cudaLaunchConfig_t lc;
-    memset(&lc, 0, sizeof lc);
+    cudaLaunchConfig_t lc = {};
     lc.gridDim = dim3((unsigned)grid); lc.blockDim = dim3(D2D_POL_THREADS);
     lc.dynamicSmemBytes = sizeof(D2dPolicySmem); lc.stream = (cudaStream_t)stream;
     cudaLaunchAttribute attr[1];
