@@ -179,6 +179,9 @@ __global__ void __launch_bounds__(D2D_BLOCK, D2D_MIN_BLOCKS) d2d_step_kernel(con
     const int64_t blk = (int64_t)blockIdx.x - 2 * p.refill_blocks;
     const int64_t i = blk * D2D_BLOCK + tid;
     const bool valid = i < p.n;
+    const unsigned vmask = __ballot_sync(0xffffffffu, valid);       // the lanes of this warp that own an environment
+    const int lane = tid & 31;
+    bool rewrite_row = false;                                        // this lane's row changed after the early store (episode swap)
 
     if (valid) {
         EnvState s;
@@ -234,6 +237,23 @@ __global__ void __launch_bounds__(D2D_BLOCK, D2D_MIN_BLOCKS) d2d_step_kernel(con
         ObsAux ax;
         const long long t_scan = clock64();
         observe(v, c, s, rc0, rs0, nr, put, ax, &s_coef[tid]);
+        // The warp's 32 observation rows are contiguous in the output ([N][27] float32): store them now, coalesced,
+        // instead of at block end -- when the outputs live in mapped host memory (d2d_step_host) the PCIe writes
+        // then start while reward / swap and the block's slower warps are still running.
+        __syncwarp(vmask);
+        {
+            const int64_t w0 = blk * D2D_BLOCK + (tid & ~31);
+            const float *src = &s_obs[(tid & ~31) * D2D_OBS_DIM];
+            float *dst = p.obs + w0 * D2D_OBS_DIM;
+            if (vmask == 0xffffffffu) {
+                const float4 *s4 = reinterpret_cast<const float4 *>(src);
+                float4 *d4 = reinterpret_cast<float4 *>(dst);
+                for (int k = lane; k < 32 * D2D_OBS_DIM / 4; k += 32) __stcs(&d4[k], s4[k]);   // streamed: read by the policy, not by the next step
+            } else {
+                const int nv = __popc(vmask);                      // last warp of the batch: lanes 0..nv-1 own an env
+                for (int k = lane; k < nv * D2D_OBS_DIM; k += nv) dst[k] = src[k];
+            }
+        }
         const long long t_obs = clock64();
 
         StepResult r;
@@ -295,6 +315,7 @@ __global__ void __launch_bounds__(D2D_BLOCK, D2D_MIN_BLOCKS) d2d_step_kernel(con
                     const float *sob = p.stg_obs + i * D2D_OBS_DIM;
 #pragma unroll
                     for (int j = 0; j < D2D_OBS_DIM; j++) row[j] = sob[j];
+                    rewrite_row = true;
                 } else {
                     // slot not ready (episode ended one step after the previous one, or state was
                     // injected): sample in the lane, into the live table buffer
@@ -304,6 +325,7 @@ __global__ void __launch_bounds__(D2D_BLOCK, D2D_MIN_BLOCKS) d2d_step_kernel(con
                     new_flags = D2D_F_INIT;
                     new_flags |= first_observation<PER_ENV>(p, &s_tab, i, nx, ny, na, n_obs, par, row, nullptr, nullptr,
                                                             next_ep, &s_coef[tid]);
+                    rewrite_row = true;
                 }
                 spawn(s, c, nx, ny, na);
                 s.flags = new_flags; s.episode = next_ep; s.n_obs = n_obs;
@@ -364,17 +386,15 @@ __global__ void __launch_bounds__(D2D_BLOCK, D2D_MIN_BLOCKS) d2d_step_kernel(con
     }
     __syncthreads();
 
-    // coalesced store of the block's [BLOCK][27] float32 observation tile
+    // rows of envs that swapped in a new episode: their first observation replaces the terminal one that was
+    // stored early (27 lanes, one coalesced 108-byte store per row)
     {
-        const int64_t base = blk * D2D_BLOCK;
-        const int rows = (int)min((int64_t)D2D_BLOCK, p.n - base);
-        if (rows == D2D_BLOCK) {
-            const float4 *src = reinterpret_cast<const float4 *>(s_obs);
-            float4 *dst = reinterpret_cast<float4 *>(p.obs + base * D2D_OBS_DIM);
-            for (int k = tid; k < D2D_BLOCK * D2D_OBS_DIM / 4; k += D2D_BLOCK) __stcs(&dst[k], src[k]);   // streamed: read by the policy, not by the next step
-        } else if (rows > 0) {
-            float *dst = p.obs + base * D2D_OBS_DIM;
-            for (int k = tid; k < rows * D2D_OBS_DIM; k += D2D_BLOCK) dst[k] = s_obs[k];
+        unsigned m = __ballot_sync(0xffffffffu, rewrite_row);
+        while (m) {
+            const int src = __ffs(m) - 1;
+            m &= m - 1;
+            if (lane < D2D_OBS_DIM)
+                p.obs[(blk * D2D_BLOCK + (tid & ~31) + src) * D2D_OBS_DIM + lane] = s_obs[((tid & ~31) + src) * D2D_OBS_DIM + lane];
         }
     }
     if (s_any_done && (tid < 14 || tid == 15)) atomicAdd(&p.stats[tid], s_stats[tid]);
