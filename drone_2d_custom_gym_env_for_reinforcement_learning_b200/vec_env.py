@@ -194,6 +194,7 @@ class Drone2dVecEnv:
             m = mask.to(device=self.device, dtype=torch.uint8).contiguous()
         _lib.check(self._L.d2d_reset(self._h, m.data_ptr() if m is not None else None, self.obs.data_ptr(),
                                      self._stream()))
+        self._host_stepped = False
         return self.obs
 
     def step_device(self, actions=None, auto_reset=True, terminal_obs=True):
