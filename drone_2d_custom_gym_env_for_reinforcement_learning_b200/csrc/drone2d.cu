@@ -40,6 +40,20 @@ struct ViewOf<false> {
     }
 };
 
+// The staging slot of an env is published by a refill lane (stage_observe) and may be consumed by the env's
+// main lane in the SAME launch: the publication is a release store of stg_meta, the consumer reads stg_meta
+// with acquire semantics and the slot's payload through L2 (never a stale L1 line).
+__device__ __forceinline__ void st_release_int4(int4 *ptr, int4 v)
+{
+    asm volatile("st.release.gpu.global.v4.s32 [%0], {%1, %2, %3, %4};" ::"l"(ptr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ int4 ld_acquire_int4(const int4 *ptr)
+{
+    int4 v;
+    asm volatile("ld.acquire.gpu.global.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(ptr) : "memory");
+    return v;
+}
+
 __device__ __forceinline__ void stage_shared_tables(const D2dParams &p, D2dSharedTables *dst, int tid, int nthreads)
 {
     const int *src = reinterpret_cast<const int *>(p.shared);
@@ -104,8 +118,7 @@ __device__ __forceinline__ void stage_observe(const D2dParams &p, const D2dShare
     const double2 xy = p.stg_xy[e];
     const int latch = first_observation<PER_ENV>(p, tab, e, xy.x, xy.y, p.stg_an[e].x, sm.y, par,
                                                  p.stg_obs + e * D2D_OBS_DIM, nullptr, nullptr, target, coef);
-    __threadfence();
-    p.stg_meta[e] = make_int4(target, sm.y, latch, target);
+    st_release_int4(&p.stg_meta[e], make_int4(target, sm.y, latch, target));
 }
 
 // The fused step: thrust -> cpSpaceStep -> sensor overlap -> nearest-3 ->
@@ -120,7 +133,7 @@ __device__ __forceinline__ void stage_observe(const D2dParams &p, const D2dShare
 template <bool PER_ENV>
 __global__ void __launch_bounds__(D2D_BLOCK, D2D_MIN_BLOCKS) d2d_step_kernel(const __grid_constant__ D2dParams p)
 {
-    __shared__ float s_obs[D2D_BLOCK * D2D_OBS_DIM];
+    __shared__ __align__(16) float s_obs[D2D_BLOCK * D2D_OBS_DIM];   // read back as float4 by the coalesced row store
     __shared__ double s_stats[D2D_STATS_DOUBLES];
     __shared__ int s_any_done;
     __shared__ D2dSharedTables s_tab;
@@ -298,7 +311,7 @@ __global__ void __launch_bounds__(D2D_BLOCK, D2D_MIN_BLOCKS) d2d_step_kernel(con
                     for (int j = 0; j < D2D_OBS_DIM; j++) t[j] = row[j];
                 }
                 const int next_ep = s.episode + 1;
-                const int4 sm = p.stg_meta[i];
+                const int4 sm = ld_acquire_int4(&p.stg_meta[i]);
                 double nx, ny, na;
                 int n_obs, new_flags;
                 if (sm.x == next_ep) {
@@ -307,14 +320,14 @@ __global__ void __launch_bounds__(D2D_BLOCK, D2D_MIN_BLOCKS) d2d_step_kernel(con
                     // first observation are taken here.  (Copying ~0.8 KB once per episode keeps the
                     // per-step working set dense: with a per-env buffer flip, live and staged rows of
                     // neighbouring envs share cache lines and the table traffic doubles.)
-                    const double2 xy = p.stg_xy[i];
-                    nx = xy.x; ny = xy.y; na = p.stg_an[i].x;
+                    const double2 xy = __ldcg(&p.stg_xy[i]);
+                    nx = xy.x; ny = xy.y; na = __ldcg(&p.stg_an[i]).x;
                     n_obs = sm.y;
                     new_flags = D2D_F_INIT | (sm.z ? D2D_F_LATCHED : 0);
                     if (PER_ENV) s_swap[tid] = n_obs;                // tables are copied by the whole warp, below
                     const float *sob = p.stg_obs + i * D2D_OBS_DIM;
 #pragma unroll
-                    for (int j = 0; j < D2D_OBS_DIM; j++) row[j] = sob[j];
+                    for (int j = 0; j < D2D_OBS_DIM; j++) row[j] = __ldcg(&sob[j]);
                     rewrite_row = true;
                 } else {
                     // slot not ready (episode ended one step after the previous one, or state was
@@ -928,6 +941,8 @@ int d2d_step(d2d_env *e, const float *actions_dev, float *obs_dev, float *reward
     if (!e) return fail(D2D_EINVAL, "handle is NULL");
     if (!e->tables_set) return fail(D2D_ESTATE, "test mode: call d2d_set_scenario before d2d_step");
     if (!obs_dev || !reward_dev || !done_dev) return fail(D2D_EINVAL, "obs/reward/done must be non-NULL");
+    if (((uintptr_t)obs_dev & 15) != 0) return fail(D2D_EINVAL, "obs_dev must be 16-byte aligned (rows are stored as 128-bit words)");
+    if (actions_dev && ((uintptr_t)actions_dev & 7) != 0) return fail(D2D_EINVAL, "actions_dev must be 8-byte aligned");
     DeviceGuard guard(e->device);
     D2dParams p = e->p;
     p.actions = actions_dev; p.obs = obs_dev; p.reward = reward_dev; p.done = done_dev;
@@ -982,12 +997,6 @@ int d2d_step_host_ex(d2d_env *e, const float *actions_host, float *obs_host, flo
     DeviceGuard guard(e->device);
     const int64_t n = e->lay.n;
     const size_t b_act = n * 2 * sizeof(float), b_obs = n * D2D_OBS_DIM * sizeof(float), b_rew = n * sizeof(float);
-    if (!e->d_obs) {
-        CUDA_TRY(cudaMalloc(&e->d_act, b_act)); CUDA_TRY(cudaMalloc(&e->d_obs, b_obs));
-        CUDA_TRY(cudaMalloc(&e->d_rew, b_rew)); CUDA_TRY(cudaMalloc(&e->d_done, n));
-        CUDA_TRY(cudaHostAlloc(&e->h_act, b_act, cudaHostAllocDefault)); CUDA_TRY(cudaHostAlloc(&e->h_obs, b_obs, cudaHostAllocDefault));
-        CUDA_TRY(cudaHostAlloc(&e->h_rew, b_rew, cudaHostAllocDefault)); CUDA_TRY(cudaHostAlloc(&e->h_done, n, cudaHostAllocDefault));
-    }
     cudaStream_t st = (cudaStream_t)stream;
     // Page-locked caller buffers (cudaHostAlloc / cudaHostRegister / torch pin_memory) are used
     // directly; pageable ones go through the handle's pinned staging buffers.
@@ -1013,6 +1022,24 @@ int d2d_step_host_ex(d2d_env *e, const float *actions_host, float *obs_host, flo
             return D2D_OK;
         }
         (void)cudaGetLastError();                // not mapped (registered without the mapped flag): copy path below
+    }
+    // copy path: device + page-locked staging buffers of the handle, allocated on first use (all or nothing)
+    if (!e->d_obs) {
+        cudaError_t err = cudaMalloc(&e->d_act, b_act);
+        if (!err) err = cudaMalloc(&e->d_rew, b_rew);
+        if (!err) err = cudaMalloc(&e->d_done, n);
+        if (!err) err = cudaHostAlloc(&e->h_act, b_act, cudaHostAllocDefault);
+        if (!err) err = cudaHostAlloc(&e->h_obs, b_obs, cudaHostAllocDefault);
+        if (!err) err = cudaHostAlloc(&e->h_rew, b_rew, cudaHostAllocDefault);
+        if (!err) err = cudaHostAlloc(&e->h_done, n, cudaHostAllocDefault);
+        if (!err) err = cudaMalloc(&e->d_obs, b_obs);            // last: d_obs != NULL marks the complete set
+        if (err) {
+            cudaFree(e->d_act); cudaFree(e->d_rew); cudaFree(e->d_done); cudaFree(e->d_obs);
+            cudaFreeHost(e->h_act); cudaFreeHost(e->h_obs); cudaFreeHost(e->h_rew); cudaFreeHost(e->h_done);
+            e->d_act = e->d_rew = e->d_obs = nullptr; e->d_done = nullptr;
+            e->h_act = e->h_obs = e->h_rew = nullptr; e->h_done = nullptr;
+            return fail(D2D_ECUDA, "d2d_step_host: staging buffers: %s", cudaGetErrorString(err));
+        }
     }
     const float *dact = nullptr;
     if (actions_host) {

@@ -341,7 +341,10 @@ class Drone2dVecEnv:
         """float64 copy of env `index`'s newest observation, wherever the last step left it."""
         if self._host_stepped:
             return self._np_out[self._flip][0][index].astype(np.float64)
-        return (self.obs64 if self.obs64 is not None else self.obs)[index].double().cpu().numpy()
+        # the float64 tap keeps the TERMINAL observation of an env that finished in the last step (what the parity
+        # tests compare); its current observation (first of the new episode) exists in float32 only
+        use64 = self.obs64 is not None and not bool(self.dones[index].item())
+        return (self.obs64 if use64 else self.obs)[index].double().cpu().numpy()
 
     def get_images(self, indices=None, pixels=325):
         """SB3 VecEnv.get_images: one frame per env (bounded to the first 16 unless `indices` is given)."""
