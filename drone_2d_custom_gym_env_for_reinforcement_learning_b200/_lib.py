@@ -25,6 +25,7 @@ EXPORTS = [
     "d2d_set_taps", "d2d_set_info_done_only", "d2d_get_state", "d2d_set_state", "d2d_episode_stats", "d2d_episode_stats_dev",
     "d2d_debug_closest_u", "d2d_debug_role_cycles", "d2d_debug_skip_physics", "d2d_launch_count", "d2d_set_stage", "d2d_gae",
     "d2d_policy_weights_bytes", "d2d_policy_pack", "d2d_policy_act", "d2d_rollout",
+    "d2d_policy_act_ex", "d2d_policy_value", "d2d_rollout_collect", "d2d_set_flight_path_ring",
 ]
 
 
@@ -78,6 +79,7 @@ def load():
     L.d2d_step_host_ex.argtypes = [vp, vp, vp, vp, vp, vp, i32, vp]
     L.d2d_set_taps.argtypes = [vp, vp, vp]
     L.d2d_set_info_done_only.argtypes = [vp, i32]
+    L.d2d_set_flight_path_ring.argtypes = [vp, vp, i32]
     L.d2d_get_state.argtypes = [vp, dp]
     L.d2d_set_state.argtypes = [vp, dp]
     L.d2d_episode_stats.argtypes = [vp, dp, i32]
@@ -90,6 +92,9 @@ def load():
     L.d2d_policy_pack.argtypes = [vp] * 8
     L.d2d_policy_act.argtypes = [vp, vp, vp, vp, i32, u64, vp]
     L.d2d_rollout.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, u64, vp]
+    L.d2d_policy_act_ex.argtypes = [vp, vp, vp, vp, vp, vp, i32, u64, vp]
+    L.d2d_policy_value.argtypes = [vp, vp, vp, vp, i64, vp]
+    L.d2d_rollout_collect.argtypes = [vp, vp, vp, i32] + [vp] * 9 + [C.c_float, C.c_float, u64, vp]
     L.d2d_launch_count.argtypes = [vp]
     L.d2d_launch_count.restype = i64
     for name in EXPORTS:

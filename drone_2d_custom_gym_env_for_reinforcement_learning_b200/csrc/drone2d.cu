@@ -232,6 +232,8 @@ __global__ void __launch_bounds__(D2D_BLOCK, D2D_MIN_BLOCKS) d2d_step_kernel(con
         }
         s.steps += 1;                                               // env:407
         store_bodies(p, i, s);
+        if (p.path_ring)                                            // env:410-415: add_postion_to_flight_path (x, H - y)
+            p.path_ring[(int64_t)((s.steps - 1) % p.path_ring_len) * p.np + i] = make_float2((float)s.px[0], (float)(c.H - s.py[0]));
         const long long t_phys = clock64();
 
         float *row = &s_obs[tid * D2D_OBS_DIM];
@@ -1002,7 +1004,8 @@ int d2d_step_host_ex(d2d_env *e, const float *actions_host, float *obs_host, flo
     // directly; pageable ones go through the handle's pinned staging buffers.
     const bool pin_a = actions_host && is_pinned_host(actions_host);
     const bool pin_o = is_pinned_host(obs_host), pin_r = is_pinned_host(reward_host), pin_d = is_pinned_host(done_host);
-    if (pin_o && pin_r && pin_d && (!actions_host || pin_a)) {
+    static const bool force_copy = getenv("D2D_HOST_COPY") && getenv("D2D_HOST_COPY")[0] == '1';   // A/B switch (tools/e2e_ab.py)
+    if (!force_copy && pin_o && pin_r && pin_d && (!actions_host || pin_a)) {
         // All caller buffers are page-locked: the kernel reads the actions from them and writes its
         // outputs into them directly (mapped host memory).  The PCIe writes of the blocks that finish
         // early overlap the rest of the launch, and three copies + their launch latencies disappear:
@@ -1147,15 +1150,13 @@ int d2d_policy_pack(const float *w0, const float *b0, const float *w1, const flo
     memcpy(p->w2, w2, sizeof p->w2);
     p->b2[0] = b2[0]; p->b2[1] = b2[1];
     p->std[0] = expf(log_std[0]); p->std[1] = expf(log_std[1]);
+    p->log_std[0] = log_std[0]; p->log_std[1] = log_std[1];
     return D2D_OK;
 }
 
-int d2d_policy_act(d2d_env *e, const void *packed_weights_dev, const float *obs_dev, float *actions_dev, int stochastic,
-                   uint64_t policy_step, void *stream)
+static int launch_policy(d2d_env *e, const void *packed_weights_dev, const float *obs_dev, D2dPolicyOut out, int64_t n_rows,
+                         int stochastic, uint64_t policy_step, void *stream)
 {
-    if (!e || !packed_weights_dev || !obs_dev || !actions_dev) return fail(D2D_EINVAL, "NULL argument");
-    DeviceGuard guard(e->device);
-    const int64_t n = e->lay.n;
     if (e->policy_grid_cap == 0) {
         // persistent CTAs, two per SM (shared memory: 115.6 KB each; TMEM: 128 of 512 columns each)
         CUDA_TRY(cudaFuncSetAttribute(d2d_policy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(D2dPolicySmem)));
@@ -1163,7 +1164,7 @@ int d2d_policy_act(d2d_env *e, const void *packed_weights_dev, const float *obs_
         CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, e->device));
         e->policy_grid_cap = 2 * sms;
     }
-    const int64_t tiles = (n + D2D_POL_TILE - 1) / D2D_POL_TILE;
+    const int64_t tiles = (n_rows + D2D_POL_TILE - 1) / D2D_POL_TILE;
     const int grid = (int)(tiles < e->policy_grid_cap ? tiles : e->policy_grid_cap);
     // programmatic dependent launch: the CTAs may become resident and set themselves up (barriers, TMEM, weight
     // image) while the preceding step kernel drains; they read `obs` only after griddepcontrol.wait
@@ -1174,11 +1175,36 @@ int d2d_policy_act(d2d_env *e, const void *packed_weights_dev, const float *obs_
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     lc.attrs = attr; lc.numAttrs = 1;
-    CUDA_TRY(cudaLaunchKernelEx(&lc, d2d_policy_kernel, (const D2dPolicyImage *)packed_weights_dev, obs_dev, actions_dev, n, stochastic,
+    CUDA_TRY(cudaLaunchKernelEx(&lc, d2d_policy_kernel, (const D2dPolicyImage *)packed_weights_dev, obs_dev, out, n_rows, stochastic,
                                 e->p.c.seed_lo, e->p.c.seed_hi, e->p.c.env_id_base, (uint64_t)policy_step));
     e->launches++;
     CUDA_TRY(cudaGetLastError());
     return D2D_OK;
+}
+
+int d2d_policy_act(d2d_env *e, const void *packed_weights_dev, const float *obs_dev, float *actions_dev, int stochastic,
+                   uint64_t policy_step, void *stream)
+{
+    return d2d_policy_act_ex(e, packed_weights_dev, obs_dev, actions_dev, nullptr, nullptr, stochastic, policy_step, stream);
+}
+
+int d2d_policy_act_ex(d2d_env *e, const void *packed_weights_dev, const float *obs_dev, float *actions_dev,
+                      float *actions_raw_dev, float *log_prob_dev, int stochastic, uint64_t policy_step, void *stream)
+{
+    if (!e || !packed_weights_dev || !obs_dev || !actions_dev) return fail(D2D_EINVAL, "NULL argument");
+    DeviceGuard guard(e->device);
+    D2dPolicyOut out = {actions_dev, actions_raw_dev, log_prob_dev, nullptr};
+    return launch_policy(e, packed_weights_dev, obs_dev, out, e->lay.n, stochastic, policy_step, stream);
+}
+
+int d2d_policy_value(d2d_env *e, const void *packed_value_weights_dev, const float *obs_dev, float *values_dev, int64_t n_rows,
+                     void *stream)
+{
+    if (!e || !packed_value_weights_dev || !obs_dev || !values_dev) return fail(D2D_EINVAL, "NULL argument");
+    if (n_rows < 1) return fail(D2D_EINVAL, "n_rows must be >= 1");
+    DeviceGuard guard(e->device);
+    D2dPolicyOut out = {nullptr, nullptr, nullptr, values_dev};
+    return launch_policy(e, packed_value_weights_dev, obs_dev, out, n_rows, 0, 0, stream);
 }
 
 int d2d_rollout(d2d_env *e, const void *packed_weights_dev, float *obs_dev, float *actions_dev, float *reward_dev,
@@ -1193,6 +1219,37 @@ int d2d_rollout(d2d_env *e, const void *packed_weights_dev, float *obs_dev, floa
         if (rc) return rc;
     }
     return D2D_OK;
+}
+
+int d2d_rollout_collect(d2d_env *e, const void *actor_weights_dev, const void *critic_weights_dev, int n_steps, float *obs_buf_dev,
+                        float *actions_dev, float *log_probs_dev, float *rewards_dev, uint8_t *dones_dev, float *values_dev,
+                        float *advantages_dev, float *returns_dev, float *action_scratch_dev, float gamma, float gae_lambda,
+                        uint64_t policy_step0, void *stream)
+{
+    if (!e || !actor_weights_dev || !critic_weights_dev || !obs_buf_dev || !actions_dev || !log_probs_dev || !rewards_dev ||
+        !dones_dev || !values_dev || !advantages_dev || !returns_dev || !action_scratch_dev)
+        return fail(D2D_EINVAL, "NULL argument");
+    if (n_steps < 1) return fail(D2D_EINVAL, "n_steps must be >= 1");
+    const int64_t n = e->lay.n;
+    const int T = n_steps;
+    for (int t = 0; t < T; t++) {
+        float *obs_t = obs_buf_dev + (int64_t)t * n * D2D_OBS_DIM;
+        // SB3 collect_rollouts: sample from the current policy, store the UNclipped action and its log-probability,
+        // step the env with the clipped one
+        int rc = d2d_policy_act_ex(e, actor_weights_dev, obs_t, action_scratch_dev, actions_dev + (int64_t)t * n * 2,
+                                   log_probs_dev + (int64_t)t * n, 1, policy_step0 + (uint64_t)t, stream);
+        if (rc) return rc;
+        // ... and the step kernel writes observation t+1, reward t and done t (= episode start t+1) straight into the rollout
+        rc = d2d_step(e, action_scratch_dev, obs_t + n * D2D_OBS_DIM, rewards_dev + (int64_t)t * n, dones_dev + (int64_t)(t + 1) * n,
+                      nullptr, 1, stream);
+        if (rc) return rc;
+    }
+    // the critic over all T + 1 stored observations in ONE launch (the weights do not change during a rollout, so this
+    // equals SB3's per-step values); row T gives the bootstrap values
+    int rc = d2d_policy_value(e, critic_weights_dev, obs_buf_dev, values_dev, (int64_t)(T + 1) * n, stream);
+    if (rc) return rc;
+    return d2d_gae(rewards_dev, values_dev, dones_dev, values_dev + (int64_t)T * n, dones_dev + (int64_t)T * n, T, n, gamma,
+                   gae_lambda, advantages_dev, returns_dev, stream);
 }
 
 int d2d_set_stage(d2d_env *e, int stage, double spawn_chance)
@@ -1217,6 +1274,16 @@ int d2d_gae(const float *rewards_dev, const float *values_dev, const uint8_t *ep
         rewards_dev, values_dev, episode_starts_dev, last_values_dev, last_dones_dev, n_steps, n_envs, gamma, gae_lambda,
         advantages_dev, returns_dev);
     CUDA_TRY(cudaGetLastError());
+    return D2D_OK;
+}
+
+int d2d_set_flight_path_ring(d2d_env *e, float *ring_dev, int ring_len)
+{
+    if (!e) return fail(D2D_EINVAL, "handle is NULL");
+    if (ring_dev && ring_len < 1) return fail(D2D_EINVAL, "ring_len must be >= 1");
+    if (ring_dev && ((uintptr_t)ring_dev & 7) != 0) return fail(D2D_EINVAL, "ring_dev must be 8-byte aligned");
+    e->p.path_ring = (float2 *)ring_dev;
+    e->p.path_ring_len = ring_dev ? ring_len : 0;
     return D2D_OK;
 }
 

@@ -178,6 +178,8 @@ struct D2dParams {
     uint8_t *done;
     const uint8_t *mask;
     double *obs64, *info, *stats;
+    float2 *path_ring;                 // optional [path_ring_len][np] (x, H - y) of the frame after every step (env:984-986), or NULL
+    int path_ring_len;
     unsigned long long *role_cycles;   // [8] max clock64 span per role/phase of the last launches (profiling hook)
     int info_done_only;                // write an env's info row only on the step that ends its episode (d2d_set_info_done_only)
     int skip_physics;                  // debug: take the pose/velocity in the state as the result of space.step (d2d_debug_skip_physics)

@@ -40,6 +40,8 @@ struct D2dPolicyImage {
     float w2[2 * D2D_POL_H];
     float b2[2];
     float std[2];
+    float log_std[2];
+    float pad_[2];
 };
 
 __host__ __device__ inline float d2d_tf32_hi(float x)
@@ -172,8 +174,17 @@ __device__ __forceinline__ void d2d_policy_fetch(const float *__restrict__ obs, 
     }
 }
 
+// What the last stage of the kernel writes per row:
+//   actor mode (values == nullptr): actions = clip(mean + std * eps, -1, 1) (what the env is stepped with, SB3 clips for
+//       the env only), actions_raw = mean + std * eps and log_prob = sum_d log N(raw_d; mean_d, std_d) if non-null
+//       (SB3 `policy.forward`, what the PPO rollout buffer stores, main.py:190-208);
+//   value mode (values != nullptr): values = output 0 of the head (the critic tower packed like an actor, row 1 = 0).
+struct D2dPolicyOut {
+    float *actions, *actions_raw, *log_prob, *values;
+};
+
 __global__ void __launch_bounds__(D2D_POL_THREADS, 2) d2d_policy_kernel(const D2dPolicyImage *__restrict__ image,
-                                                                        const float *__restrict__ obs, float *__restrict__ actions,
+                                                                        const float *__restrict__ obs, D2dPolicyOut out,
                                                                         int64_t n, int stochastic, uint32_t seed_lo, uint32_t seed_hi,
                                                                         int64_t env_id_base, uint64_t step_index)
 {
@@ -318,7 +329,8 @@ __global__ void __launch_bounds__(D2D_POL_THREADS, 2) d2d_policy_kernel(const D2
             const float2 other = part[row];
             mu0 += other.x + S.w.b2[0];
             mu1 += other.y + S.w.b2[1];
-            if (stochastic) {
+            float e0 = 0.0f, e1 = 0.0f;
+            if (stochastic && !out.values) {
                 uint32_t o[4];
                 philox4x32_10((uint32_t)(env_id_base + base + row), (uint32_t)step_index, (uint32_t)(step_index >> 32),
                               D2D_STREAM_POLICY, seed_lo, seed_hi, o);
@@ -328,11 +340,19 @@ __global__ void __launch_bounds__(D2D_POL_THREADS, 2) d2d_policy_kernel(const D2
                 const float rr = sqrtf(-2.0f * __logf(u1));
                 float sn, cs;
                 sincospif(2.0f * u2, &sn, &cs);
-                mu0 = fmaf(S.w.std[0], rr * cs, mu0);
-                mu1 = fmaf(S.w.std[1], rr * sn, mu1);
+                e0 = rr * cs; e1 = rr * sn;
+                mu0 = fmaf(S.w.std[0], e0, mu0);
+                mu1 = fmaf(S.w.std[1], e1, mu1);
             }
-            reinterpret_cast<float2 *>(actions)[base + row] =
-                make_float2(fminf(fmaxf(mu0, -1.0f), 1.0f), fminf(fmaxf(mu1, -1.0f), 1.0f));
+            if (out.values) {
+                out.values[base + row] = mu0;                   // value mode: the noise-free head output
+            } else {
+                if (out.actions_raw) reinterpret_cast<float2 *>(out.actions_raw)[base + row] = make_float2(mu0, mu1);
+                if (out.log_prob)                               // -(eps^2)/2 - log(std) - log(2 pi)/2, summed over the two dims
+                    out.log_prob[base + row] = -0.5f * (e0 * e0 + e1 * e1) - S.w.log_std[0] - S.w.log_std[1] - 1.8378770664093453f;
+                reinterpret_cast<float2 *>(out.actions)[base + row] =
+                    make_float2(fminf(fmaxf(mu0, -1.0f), 1.0f), fminf(fmaxf(mu1, -1.0f), 1.0f));
+            }
         }
     }
 

@@ -97,7 +97,7 @@ def run_test(agent_path, scenario, run_n_times=100, out_root="Tests", device=Non
         track.append((alive.clone(), x, H - y))
         newly = alive & (done != 0)
         if newly.any():
-            info = env.info[newly]
+            info = env.info_rows(newly)
             bits = info[:, 11].long()
             out[newly] = torch.stack([((bits & 2) != 0).double(), ((bits & 13) != 0).double(),
                                       (((bits & 1) != 0) & ((bits & 14) == 0)).double(), info[:, 9], info[:, 7],

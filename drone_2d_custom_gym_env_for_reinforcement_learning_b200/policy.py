@@ -117,7 +117,7 @@ def rollout_one_episode_each(env, actor, deterministic=False, seed=0, max_steps=
         obs, _, done = env.step_device(act, auto_reset=False, terminal_obs=False)
         newly = alive & (done != 0)
         if newly.any():
-            info = env.info[newly]
+            info = env.info_rows(newly)
             bits = info[:, 11].long()
             rec = torch.stack([((bits & 2) != 0).double(), ((bits & 13) != 0).double(),
                                (((bits & 1) != 0) & ((bits & 14) == 0)).double(), info[:, 9], info[:, 7], info[:, 10]], 1)

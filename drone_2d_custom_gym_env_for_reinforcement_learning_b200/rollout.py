@@ -1,8 +1,9 @@
 """Device-resident PPO rollout collection (the caller of `step` in the reference's training
 loop, main.py:190-208 -> SB3 `PPO.collect_rollouts`): observations, actions, rewards, episode
-starts, values and log-probabilities are written into [T, N] tensors on the GPU, advantages and
-returns come from one `d2d_gae` launch.  Nothing crosses PCIe during a rollout; the learner
-(SB3's PPO update) is out of scope.
+starts, values and log-probabilities are written into [T, N] tensors on the GPU by the hand-written
+kernels themselves (`RolloutCollector` -> `d2d_rollout_collect`), advantages and returns come from one
+`d2d_gae` launch.  Nothing crosses PCIe during a rollout; the learner (SB3's PPO update) is out of scope.
+`MlpActorCritic` is the plain torch float32 statement of the same policy (the reference the tests compare with).
 """
 import ctypes as C
 import io
@@ -86,40 +87,69 @@ def gae_reference(rewards, values, episode_starts, last_values, last_dones, gamm
     return adv, adv + values
 
 
+def pack_tower(w0, b0, w1, b1, w2, b2, log_std, device):
+    """`d2d_policy_pack` of one 27 -> 64 -> 64 -> (<= 2) tanh tower: the shared-memory image the tcgen05 kernel reads."""
+    L = _lib.load()
+    rows = [t.detach().to(torch.float32).cpu().contiguous() for t in (w0, b0, w1, b1)]
+    w2p, b2p = torch.zeros((2, 64), dtype=torch.float32), torch.zeros(2, dtype=torch.float32)
+    w2p[:w2.shape[0]] = w2.detach().float().cpu()
+    b2p[:b2.shape[0]] = b2.detach().float().cpu()
+    ls = torch.zeros(2, dtype=torch.float32) if log_std is None else log_std.detach().float().cpu().contiguous()
+    host = torch.zeros(L.d2d_policy_weights_bytes(), dtype=torch.uint8)
+    _lib.check(L.d2d_policy_pack(rows[0].data_ptr(), rows[1].data_ptr(), rows[2].data_ptr(), rows[3].data_ptr(), w2p.data_ptr(),
+                                 b2p.data_ptr(), ls.data_ptr(), host.data_ptr()))
+    return host.to(device)
+
+
 class RolloutCollector:
-    """SB3 `collect_rollouts` on the device: T steps of N environments per call."""
+    """SB3 `collect_rollouts` + `compute_returns_and_advantage` on the device, T steps of N environments per call,
+    through ONE C call (`d2d_rollout_collect`): per step the tcgen05 policy kernel (sample, unclipped action,
+    log-probability) and the step kernel, which write straight into the [T, N] tensors below; then one launch of the
+    same tcgen05 kernel evaluates the critic on all T + 1 stored observations, and one GAE launch.  No torch kernel and
+    no host work between two steps.  `policy` (MlpActorCritic) only supplies the weights."""
 
     def __init__(self, env, policy, n_steps=128, gamma=0.99, gae_lambda=0.95, seed=0):
         self.env, self.policy, self.T = env, policy, int(n_steps)
-        self.gamma, self.lam = gamma, gae_lambda
-        n, dev = env.num_envs, env.device
-        self.obs = torch.empty((self.T, n, 27), dtype=torch.float32, device=dev)
-        self.actions = torch.empty((self.T, n, 2), dtype=torch.float32, device=dev)
-        self.rewards = torch.empty((self.T, n), dtype=torch.float32, device=dev)
-        self.values = torch.empty((self.T, n), dtype=torch.float32, device=dev)
-        self.log_probs = torch.empty((self.T, n), dtype=torch.float32, device=dev)
-        self.episode_starts = torch.empty((self.T, n), dtype=torch.uint8, device=dev)
-        self.gen = torch.Generator(device=dev)
-        self.gen.manual_seed(seed)
-        self._last_obs = env.reset_device().clone()
-        self._last_starts = torch.ones(n, dtype=torch.uint8, device=dev)
+        self.gamma, self.lam = float(gamma), float(gae_lambda)
+        n, dev, T = env.num_envs, env.device, self.T
+        self._L = _lib.load()
+        self.obs_buf = torch.empty((T + 1, n, 27), dtype=torch.float32, device=dev)
+        self.actions = torch.empty((T, n, 2), dtype=torch.float32, device=dev)        # unclipped, as SB3 stores them
+        self.log_probs = torch.empty((T, n), dtype=torch.float32, device=dev)
+        self.rewards = torch.empty((T, n), dtype=torch.float32, device=dev)
+        self.dones = torch.empty((T + 1, n), dtype=torch.uint8, device=dev)
+        self.values_buf = torch.empty((T + 1, n), dtype=torch.float32, device=dev)
+        self.advantages = torch.empty((T, n), dtype=torch.float32, device=dev)
+        self.returns = torch.empty((T, n), dtype=torch.float32, device=dev)
+        self._scratch = torch.empty((n, 2), dtype=torch.float32, device=dev)
+        p = policy
+        self.actor_packed = pack_tower(p.w0, p.b0, p.w1, p.b1, p.w2, p.b2, p.log_std, dev)
+        self.critic_packed = pack_tower(p.v0, p.vb0, p.v1, p.vb1, p.v2, p.vb2, None, dev)
+        self.obs_buf[0].copy_(env.reset_device())
+        self.dones[0].fill_(1)
+        self.policy_step = int(seed) << 20
         self.num_timesteps = 0
 
+    # SB3 RolloutBuffer views
+    obs = property(lambda self: self.obs_buf[:self.T])
+    episode_starts = property(lambda self: self.dones[:self.T])
+    values = property(lambda self: self.values_buf[:self.T])
+    last_values = property(lambda self: self.values_buf[self.T])
+    last_dones = property(lambda self: self.dones[self.T])
+    last_obs = property(lambda self: self.obs_buf[self.T])
+
     def collect(self):
-        env, pol = self.env, self.policy
-        for t in range(self.T):
-            a, logp, v = pol.act(self._last_obs, self.gen)
-            self.obs[t].copy_(self._last_obs)
-            self.actions[t].copy_(a)
-            self.values[t].copy_(v)
-            self.log_probs[t].copy_(logp)
-            self.episode_starts[t].copy_(self._last_starts)
-            obs, rew, done = env.step_device(a.clamp(-1.0, 1.0), terminal_obs=False)     # SB3 clips for the env only
-            self.rewards[t].copy_(rew)
-            self._last_obs.copy_(obs)
-            self._last_starts.copy_(done)
-        self.num_timesteps += self.T * env.num_envs
-        last_values = pol.value(self._last_obs)
-        self.advantages, self.returns = gae(self.rewards, self.values, self.episode_starts, last_values,
-                                            self._last_starts, self.gamma, self.lam)
+        env, T = self.env, self.T
+        if self.num_timesteps:
+            self.obs_buf[0].copy_(self.obs_buf[T])                 # device-to-device copies between two rollouts
+            self.dones[0].copy_(self.dones[T])
+        st = C.c_void_p(torch.cuda.current_stream(env.device).cuda_stream)
+        _lib.check(self._L.d2d_rollout_collect(
+            env._h, self.actor_packed.data_ptr(), self.critic_packed.data_ptr(), T, self.obs_buf.data_ptr(),
+            self.actions.data_ptr(), self.log_probs.data_ptr(), self.rewards.data_ptr(), self.dones.data_ptr(),
+            self.values_buf.data_ptr(), self.advantages.data_ptr(), self.returns.data_ptr(), self._scratch.data_ptr(),
+            self.gamma, self.lam, self.policy_step, st))
+        self.policy_step += T
+        self.num_timesteps += T * env.num_envs
+        env._host_stepped = False
         return self

@@ -38,7 +38,7 @@ def config_from_kwargs(kwargs):
     struct d2d_config.  Unknown keys raise TypeError; the reference would raise
     KeyError for missing ones -- here missing keys take the rl_config defaults."""
     kw = dict(env_train_config)
-    extra = {"sim_num": 0}
+    extra = {"sim_num": 0, "solver_iterations": None}      # solver_iterations: pymunk Space.iterations (default 10)
     for k, v in kwargs.items():
         if k in kw:
             kw[k] = v
@@ -66,6 +66,8 @@ def config_from_kwargs(kwargs):
             scenario, kw["screensize_x"], kw["screensize_y"])
     else:
         raise ValueError("mode must be 'curriculum' or 'test', got %r" % (mode,))
+    if extra["solver_iterations"] is not None:
+        c.iterations = int(extra["solver_iterations"])
     c.n_steps = int(kw["n_steps"])
     c.n_wps = int(kw["n_wps"])
     c.spawn_corner_lo, c.spawn_corner_hi = int(kw["spawn_corners"][0]), int(kw["spawn_corners"][1])
@@ -129,13 +131,19 @@ class Drone2dVecEnv:
         _lib.check(self._L.d2d_create(C.byref(self.cfg), n, self.env_id_base, self.seed_value & (2 ** 64 - 1),
                                       dev.index if dev.index is not None else torch.cuda.current_device(),
                                       self.state.data_ptr(), nbytes.value, C.byref(self._h)))
-        self.obs64 = self.info = None
+        self.obs64 = self.info = self._np_info = None
         if info_mode == "full":
             self.enable_taps()
         elif info_mode == "episode":
             self.enable_taps(done_only=True)
         if self.cfg.mode == _lib.MODE_TEST:
             self.set_scenario(*scenario_tables(self.kwargs["scenario"], self.cfg.screen_x, self.cfg.screen_y))
+        # env:410-415: with render_path the reference appends the frame position after every step and hands the list out as
+        # info["flight_path"] when the episode ends.  Here: a device ring of the last `ring` positions per env (whole
+        # episodes when n_steps fits; bounded to ~1 GB), gathered for the envs that finish.
+        self.path_ring = None
+        if self.kwargs.get("render_path") is True and info_mode != "none":
+            self.enable_flight_paths()
         # Page-locked host buffers of the host-facing step(): the kernel reads the actions from them and writes
         # obs / reward / done / terminal observations into them directly (d2d_step_host_ex, mapped memory).
         # Two output sets alternate, so the arrays of step t stay intact until step t + 2 (see copy_outputs).
@@ -169,12 +177,50 @@ class Drone2dVecEnv:
         the step that ends its episode (all that step() needs in info_mode="episode": 22 MB less per step)."""
         n = self.num_envs
         self.obs64 = None if done_only else torch.zeros((n, 27), dtype=torch.float64, device=self.device)
-        self.info = torch.zeros((n, _lib.INFO_DOUBLES), dtype=torch.float64, device=self.device)
+        if done_only:
+            # only the rows of finishing envs are written: they go straight into page-locked host memory (mapped into
+            # the kernel's address space), so building the info dicts needs no device gather and no extra copy
+            self.info = torch.zeros((n, _lib.INFO_DOUBLES), dtype=torch.float64).pin_memory()
+            self._np_info = self.info.numpy()
+        else:
+            self.info = torch.zeros((n, _lib.INFO_DOUBLES), dtype=torch.float64, device=self.device)
+            self._np_info = None
         _lib.check(self._L.d2d_set_taps(self._h, self.obs64.data_ptr() if self.obs64 is not None else None, self.info.data_ptr()))
         _lib.check(self._L.d2d_set_info_done_only(self._h, 1 if done_only else 0))
 
+    def enable_flight_paths(self, ring=None):
+        np_ = (self.num_envs + 31) // 32 * 32
+        if ring is None:
+            ring = max(1, min(int(self.cfg.n_steps), (1 << 30) // (8 * np_)))
+        self.path_ring = torch.zeros((int(ring), np_, 2), dtype=torch.float32, device=self.device)
+        _lib.check(self._L.d2d_set_flight_path_ring(self._h, self.path_ring.data_ptr(), int(ring)))
+
+    def flight_paths_of(self, indices, steps):
+        """[(x, screen_height - y), ...] of the episodes that just ended in envs `indices` (`steps`: their lengths)."""
+        if self.path_ring is None or len(indices) == 0:
+            return [[] for _ in indices]
+        K = self.path_ring.shape[0]
+        cols = self.path_ring[:, torch.as_tensor(np.asarray(indices), device=self.device)].cpu().numpy()     # [K, m, 2]
+        out = []
+        for j, T in enumerate(steps):
+            T = int(T)
+            if T <= K:
+                rows = cols[:T, j]
+            else:                                      # only the last K positions survive, oldest first
+                rows = np.roll(cols[:, j], -(T % K), axis=0)
+            out.append([(float(x), float(y)) for x, y in rows])
+        return out
+
+    def info_rows(self, mask):
+        """Info-tap rows of the envs selected by a boolean device mask, as a float64 device tensor (wherever the tap
+        lives: device memory, or page-locked host memory in info_mode="episode")."""
+        if self.info.is_cuda:
+            return self.info[mask]
+        torch.cuda.current_stream(self.device).synchronize()      # the kernel's stores into host memory have landed
+        return self.info[mask.cpu()].to(self.device)
+
     def disable_taps(self):
-        self.obs64 = self.info = None
+        self.obs64 = self.info = self._np_info = None
         _lib.check(self._L.d2d_set_taps(self._h, None, None))
 
     def set_scenario(self, wps, us, xparams, yparams, obstacles):
@@ -260,17 +306,22 @@ class Drone2dVecEnv:
                 "flight_path": [],                 # env:612; positions are not recorded on the device
                 "episode": {"r": float(r[10]), "l": int(r[7])}}
 
+    _ROW_KEYS = INFO_KEYS + ("APE", "total_reward")          # info-tap columns 0..10
+
     def _done_infos(self, rows):
         """Info dicts of the envs that finished this step (rows: their info-tap rows), built from Python floats."""
         out = []
+        keys = self._ROW_KEYS
         for r in rows.tolist():
             bits, steps = int(r[11]), int(r[7])
-            out.append({"reward": r[0], "collision_avoidance_reward": r[1], "path_adherence": r[2], "path_progression": r[3],
-                        "collision_reward": r[4], "reach_end_reward": r[5], "agressive_alpha_reward": r[6], "env_steps": steps,
-                        "dist_closest_obs": r[8],
-                        "n_collisions": int(bool(bits & 1) and not (bits & 14)), "n_successful_runs": int(bool(bits & 2)),
-                        "n_failed_runs": int(bool(bits & 13)), "APE": r[9], "total_reward": r[10], "flight_path": [],
-                        "episode": {"r": r[10], "l": steps}})
+            d = dict(zip(keys, r))
+            d["env_steps"] = steps
+            d["n_collisions"] = int(bool(bits & 1) and not (bits & 14))      # env:595-610 overwrite order
+            d["n_successful_runs"] = int(bool(bits & 2))
+            d["n_failed_runs"] = int(bool(bits & 13))
+            d["flight_path"] = []
+            d["episode"] = {"r": r[10], "l": steps}
+            out.append(d)
         return out
 
     def _build_infos(self, dones):
@@ -282,8 +333,15 @@ class Drone2dVecEnv:
         else:
             infos = list(self._empty_infos)
             if len(idx) and self.info is not None:
-                rows = self.info[torch.from_numpy(idx).to(self.device)].cpu().numpy()
-                for i, d in zip(idx.tolist(), self._done_infos(rows)):
+                if self._np_info is not None and self._host_stepped:
+                    rows = self._np_info[idx]            # written by the kernel into page-locked host memory
+                else:
+                    rows = self.info_rows(torch.from_numpy(dones).to(self.device)).cpu().numpy()
+                done_infos = self._done_infos(rows)
+                if self.path_ring is not None:
+                    for d, fp in zip(done_infos, self.flight_paths_of(idx, rows[:, 7])):
+                        d["flight_path"] = fp
+                for i, d in zip(idx.tolist(), done_infos):
                     infos[i] = d
             else:
                 for i in idx:

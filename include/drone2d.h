@@ -147,6 +147,13 @@ int d2d_set_taps(d2d_env *env, double *obs64_dev, double *info_dev);
  * rows SB3 reads: infos of finished envs); 0 (default): every env, every step. */
 int d2d_set_info_done_only(d2d_env *env, int enable);
 
+/* Optional recording of the flight path (env:410-415 `add_postion_to_flight_path`, read back as
+ * info["flight_path"] at env:612 and main.py:276): ring_dev float32 [ring_len][np][2] with np = n rounded up to a
+ * multiple of 32; after every step the kernel stores (x, screen_y - y) of the frame at row (step counter - 1) %
+ * ring_len, so the rows 0..T-1 of a column hold the T positions of the episode that just ended (its last ring_len
+ * positions if T > ring_len) until the next step.  NULL switches the recording off (default). */
+int d2d_set_flight_path_ring(d2d_env *env, float *ring_dev, int ring_len);
+
 /* State blob (HOST, float64 [n][D2D_STATE_DOUBLES], sync): per env
  *   [0..17]  frame, left motor, right motor: px, py, vx, vy, angle, omega
  *   [18..29] cached pivot impulses jx,jy of left_1..3, right_1..3
@@ -190,12 +197,41 @@ int d2d_policy_pack(const float *w0, const float *b0, const float *w1, const flo
 int d2d_policy_act(d2d_env *env, const void *packed_weights_dev, const float *obs_dev, float *actions_dev,
                    int stochastic, uint64_t policy_step, void *stream);
 
+/* The same evaluation with everything a PPO rollout buffer stores (SB3 `policy.forward` inside
+ * `collect_rollouts`, the loop main.py:190-208 runs): actions_dev receives the clipped action the env is stepped
+ * with, actions_raw_dev (or NULL) the unclipped sample mean + std * eps, log_prob_dev (or NULL) its log-probability
+ * under the diagonal Gaussian. */
+int d2d_policy_act_ex(d2d_env *env, const void *packed_weights_dev, const float *obs_dev, float *actions_dev,
+                      float *actions_raw_dev, float *log_prob_dev, int stochastic, uint64_t policy_step, void *stream);
+
+/* The critic of the same MlpPolicy (value tower 27 -> 64 -> 64 -> 1) on n_rows observations (float32 [n_rows][27],
+ * e.g. a whole rollout [T + 1][n]) in one launch of the tcgen05 kernel.  packed_value_weights_dev: d2d_policy_pack
+ * of the tower with w2 = [value_net.weight; 0], b2 = [value_net.bias, 0], log_std = 0. */
+int d2d_policy_value(d2d_env *env, const void *packed_value_weights_dev, const float *obs_dev, float *values_dev,
+                     int64_t n_rows, void *stream);
+
 /* Closed-loop rollout without the host in the loop: n_steps x (d2d_policy_act, d2d_step with
  * auto-reset) enqueued back to back on `stream`; obs_dev must hold the current observations on
  * entry and holds the final ones on return.  Episode statistics accumulate in the handle. */
 int d2d_rollout(d2d_env *env, const void *packed_weights_dev, float *obs_dev, float *actions_dev,
                 float *reward_dev, uint8_t *done_dev, int n_steps, int stochastic, uint64_t policy_step0,
                 void *stream);
+
+/* PPO rollout collection on the device (SB3 `collect_rollouts` + `compute_returns_and_advantage`, the loop the
+ * reference's training mode runs, main.py:190-208): n_steps x (d2d_policy_act_ex, d2d_step with auto-reset), then the
+ * critic over all stored observations and GAE, enqueued from C on `stream` -- no host work and no library kernel
+ * between two steps; the kernels write straight into the caller's rollout tensors:
+ *   obs_buf_dev   float32 [n_steps + 1][n][27]  row 0 = current observations on entry, row t + 1 written by step t
+ *   actions_dev   float32 [n_steps][n][2]       unclipped samples        log_probs_dev float32 [n_steps][n]
+ *   rewards_dev   float32 [n_steps][n]
+ *   dones_dev     uint8   [n_steps + 1][n]      row 0 = episode starts of step 0 on entry, row t + 1 written by step t
+ *                                               (rows 0..n_steps-1 are SB3's episode_starts, row n_steps its last dones)
+ *   values_dev    float32 [n_steps + 1][n]      row n_steps = bootstrap values
+ *   advantages_dev, returns_dev float32 [n_steps][n];  action_scratch_dev float32 [n][2] (clipped actions of the step) */
+int d2d_rollout_collect(d2d_env *env, const void *actor_weights_dev, const void *critic_weights_dev, int n_steps,
+                        float *obs_buf_dev, float *actions_dev, float *log_probs_dev, float *rewards_dev, uint8_t *dones_dev,
+                        float *values_dev, float *advantages_dev, float *returns_dev, float *action_scratch_dev, float gamma,
+                        float gae_lambda, uint64_t policy_step0, void *stream);
 
 /* Curriculum scheduler hook: the reference derives the stage from the newest checkpoint file
  * name every time an env is rebuilt (env:79-85, 326-372); here the trainer sets it explicitly.

@@ -92,6 +92,10 @@ def load(path):
     L.d2o_philox4x32_10.argtypes = [C.POINTER(C.c_uint), C.POINTER(C.c_uint), C.POINTER(C.c_uint)]
     L.d2o_after_physics.argtypes = [C.POINTER(State), C.POINTER(Path), C.POINTER(Obstacles), C.POINTER(Config),
                                     C.POINTER(StepOut)]
+    if hasattr(L, "d2o_frame_velocity_rollout"):
+        dp = C.POINTER(C.c_double)
+        L.d2o_frame_velocity_rollout.restype = None
+        L.d2o_frame_velocity_rollout.argtypes = [C.POINTER(State), dp, C.c_int, C.POINTER(Config), dp, dp, C.c_double]
     L.d2o_frame_touches.restype = C.c_int
     L.d2o_frame_touches.argtypes = [C.POINTER(Body), C.POINTER(Obstacles), C.POINTER(Config)]
     return L

@@ -26,6 +26,11 @@
 /* pymunk Space.damping: never set by the reference (default 1.0).  env:376-380 assigns a plain Python
  * attribute `body.damping = 0.9`, which Chipmunk never sees; tests/test_physics_pin.py checks this
  * against genuine pymunk trajectories by rebuilding the oracle with -DD2O_SPACE_DAMPING=0.9. */
+/* Further compile-time variants of the solver, used ONLY by the inverse-dynamics discriminator
+ * (tests/test_inverse_dynamics_cpu.py) to show that the genuine pymunk trajectories reject them:
+ *   -DD2O_NO_WARM_START          cached impulses are not re-applied at the start of a step
+ *   -DD2O_JOINT_ORDER_PERMUTED   joints solved right_1..3 before left_1..3 (insertion order swapped)
+ *   -DD2O_POSITIONS_AFTER        positions integrated after the velocity solve (symplectic Euler order) */
 #ifndef D2O_SPACE_DAMPING
 #define D2O_SPACE_DAMPING 1.0
 #endif
@@ -201,9 +206,11 @@ int d2o_space_step(d2o_state *s, const d2o_obstacles *ob, const d2o_config *c,
     /* 1. cpBodyUpdatePosition for bodies in insertion order. */
     double rc[3], rs[3];
     for (int i = 0; i < 3; i++) {
+#ifndef D2O_POSITIONS_AFTER
         B[i].px = B[i].px + (B[i].vx + 0.0) * dt;
         B[i].py = B[i].py + (B[i].vy + 0.0) * dt;
         B[i].a = B[i].a + (B[i].w + 0.0) * dt;
+#endif
         rc[i] = cos(B[i].a); rs[i] = sin(B[i].a);
     }
 
@@ -254,6 +261,9 @@ int d2o_space_step(d2o_state *s, const d2o_obstacles *ob, const d2o_config *c,
     }
 
     /* 6. warm start (dt_coef = dt/prev_dt = 1; on the first step every jAcc is 0). */
+#ifdef D2O_NO_WARM_START
+    for (int j = 0; j < 6; j++) { s->jx[j] = 0; s->jy[j] = 0; }
+#endif
     for (int j = 0; j < 6; j++) {
         int m = t.motor[j];
         double jx = s->jx[j] * 1.0, jy = s->jy[j] * 1.0;
@@ -265,7 +275,12 @@ int d2o_space_step(d2o_state *s, const d2o_obstacles *ob, const d2o_config *c,
 
     /* 7. sequential impulses. */
     for (int it = 0; it < c->iterations; it++) {
-        for (int j = 0; j < 6; j++) {
+        for (int jj = 0; jj < 6; jj++) {
+#ifdef D2O_JOINT_ORDER_PERMUTED
+            const int j = (jj + 3) % 6;
+#else
+            const int j = jj;
+#endif
             int m = t.motor[j];
             /* relative_velocity(a, b, r1, r2) */
             double v1x = B[m].vx + (-r1y[j]) * B[m].w, v1y = B[m].vy + r1x[j] * B[m].w;
@@ -283,6 +298,11 @@ int d2o_space_step(d2o_state *s, const d2o_obstacles *ob, const d2o_config *c,
             B[0].w += t.iinv[0] * (r2x[j] * jy - r2y[j] * jx);
         }
     }
+#ifdef D2O_POSITIONS_AFTER
+    for (int i = 0; i < 3; i++) {
+        B[i].px = B[i].px + B[i].vx * dt; B[i].py = B[i].py + B[i].vy * dt; B[i].a = B[i].a + B[i].w * dt;
+    }
+#endif
     return hit;
 }
 
@@ -631,6 +651,38 @@ void d2o_after_physics(d2o_state *s, const d2o_path *p, const d2o_obstacles *ob,
     s->total_reward += reward;
     o->end_collision = end1; o->end_reached = end2; o->end_time = end4; o->end_alpha = end5;
     o->done = end1 || end2 || end4 || end5;
+}
+
+/* Frame velocity after each of n consecutive space steps from *s0 (which is not modified) under the
+ * given actions [n][2]: the forward model of the inverse-dynamics discriminator (oracle/inverse_dynamics.py).
+ * With jac != NULL also the forward-difference Jacobian d v[2n] / d actions[2n] (row-major [2n][2n], step h). */
+void d2o_frame_velocity_rollout(const d2o_state *s0, const double *actions, int n, const d2o_config *c,
+                                double *v_out, double *jac, double h)
+{
+    d2o_obstacles none; none.n = 0;
+    d2o_state s = *s0;
+    for (int k = 0; k < n; k++) {
+        d2o_space_step(&s, &none, c, actions[2 * k], actions[2 * k + 1]);
+        v_out[2 * k] = s.body[0].vx; v_out[2 * k + 1] = s.body[0].vy;
+    }
+    if (!jac) return;
+    const int m = 2 * n;
+    for (int i = 0; i < m * m; i++) jac[i] = 0.0;
+    /* a perturbation of action k only changes steps >= k: restart from the state before step k */
+    d2o_state base = *s0;
+    for (int k = 0; k < n; k++) {
+        for (int q = 0; q < 2; q++) {
+            d2o_state t = base;
+            for (int j = k; j < n; j++) {
+                double aL = actions[2 * j], aR = actions[2 * j + 1];
+                if (j == k) { if (q == 0) aL += h; else aR += h; }
+                d2o_space_step(&t, &none, c, aL, aR);
+                jac[(2 * j) * m + 2 * k + q] = (t.body[0].vx - v_out[2 * j]) / h;
+                jac[(2 * j + 1) * m + 2 * k + q] = (t.body[0].vy - v_out[2 * j + 1]) / h;
+            }
+        }
+        d2o_space_step(&base, &none, c, actions[2 * k], actions[2 * k + 1]);
+    }
 }
 
 void d2o_env_step_batch(int n, d2o_state *s, const d2o_path *p, int path_stride,

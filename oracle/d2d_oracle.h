@@ -143,6 +143,11 @@ void d2o_after_physics(d2o_state *s, const d2o_path *p, const d2o_obstacles *ob,
  * (width x height/2, Drone.py:16) touches any obstacle circle. */
 int d2o_frame_touches(const d2o_body *frame, const d2o_obstacles *ob, const d2o_config *c);
 
+/* Forward model of the inverse-dynamics discriminator: frame velocity after each of n steps from *s0
+ * (unmodified) under actions [n][2]; jac (or NULL) receives the forward-difference Jacobian [2n][2n]. */
+void d2o_frame_velocity_rollout(const d2o_state *s0, const double *actions, int n, const d2o_config *c,
+                                double *v_out, double *jac, double h);
+
 /* Batch helpers (AoS arrays of n envs; path/obstacles either shared (stride 0)
  * or per env (stride 1)); actions float32 [n,2] like the gym boundary. */
 void d2o_env_step_batch(int n, d2o_state *s, const d2o_path *p, int path_stride,

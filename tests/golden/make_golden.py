@@ -22,7 +22,7 @@ inputs + outputs.  The fixtures pin:
   transforms.json     ssa / R_w_b (transformations.py:6-11)
   closed_loop.json    the reference's own evaluation artefacts
                       Tests/<setting>/test_k/results.txt (statistical fixtures)
-  agent_19_policy.npz actor weights of ppo_agents/PFCA_see_3_obs_19_90.zip
+  agent_19_policy.npz actor weights of ppo_agents/PFCA_see_3_obs_19_90.zip (agent_19_value.npz: its critic)
                       (data, not source; needed on the GPU box where the
                       reference tree does not exist)
 
@@ -205,6 +205,10 @@ def gen_policy():
             if k.startswith(("mlp_extractor.policy_net", "action_net", "log_std"))}
     np.savez(os.path.join(HERE, "agent_19_policy.npz"), **keep)
     print("wrote agent_19_policy.npz", {k: v.shape for k, v in keep.items()})
+    # the critic of the same checkpoint (value tower of the SB3 MlpPolicy): used by the rollout-collection tests
+    val = {k.replace(".", "__"): v.numpy() for k, v in sd.items() if k.startswith(("mlp_extractor.value_net", "value_net"))}
+    np.savez(os.path.join(HERE, "agent_19_value.npz"), **val)
+    print("wrote agent_19_value.npz", {k: v.shape for k, v in val.items()})
 
 
 if __name__ == "__main__":

@@ -163,3 +163,43 @@ def test_host_step_zero_copy_views_alternate(pkg):
             assert np.array_equal(ia[i]["terminal_observation"], ib[i]["terminal_observation"])
             assert not np.array_equal(ia[i]["terminal_observation"], oa[i])   # obs already belongs to the next episode
     a.close(); b.close()
+
+
+def test_flight_path_in_infos_when_render_path_is_set():
+    """env:410-415,612: with render_path the finished episode's frame positions (x, screen_height - y), one per
+    step, come back as info["flight_path"] (read at main.py:276).  Device ring -> gathered for finishing envs."""
+    pkg = importlib.import_module(PKG)
+    n, T = 96, 25
+    env = pkg.Drone2dVecEnv(n, seed=5, mode="test", scenario="corridor", render_path=True, n_steps=T)
+    assert env.path_ring is not None and env.path_ring.shape[0] == T
+    env.reset()
+    rng = np.random.RandomState(0)
+    track = [[] for _ in range(n)]
+    seen = 0
+    for t in range(2 * T + 3):
+        pre_steps = env.get_state()[:, 32].copy()
+        obs, rew, dones, infos = env.step(rng.uniform(-1, 1, (n, 2)).astype(np.float32))
+        st = env.get_state()
+        for i in range(n):
+            if dones[i]:
+                fp = infos[i]["flight_path"]
+                assert len(fp) == infos[i]["env_steps"] == int(pre_steps[i]) + 1
+                ref = np.array(track[i], dtype=np.float64).reshape(-1, 2)
+                got = np.array(fp)
+                assert np.abs(got[:-1] - ref).max() < 1e-3 if len(ref) else True      # float32 ring vs float64 state
+                # the last point is the terminal position: consistent with the terminal observation (obs[6:8])
+                tobs = infos[i]["terminal_observation"]
+                assert abs((tobs[6] + 1) * 650.0 - got[-1, 0]) < 0.05 and abs(1300.0 - (tobs[7] + 1) * 650.0 - got[-1, 1]) < 0.05
+                track[i] = []
+                seen += 1
+            else:
+                track[i].append((st[i, 0], 1300.0 - st[i, 1]))
+    assert seen >= 2 * n
+    env.close()
+    # off by default (training configuration): no ring, info key present and empty
+    env = pkg.Drone2dVecEnv(8, seed=5, mode="test", scenario="corridor", n_steps=3)
+    env.reset()
+    for _ in range(3):
+        _, _, dones, infos = env.step(np.zeros((8, 2), np.float32))
+    assert dones.all() and infos[0]["flight_path"] == [] and env.path_ring is None
+    env.close()

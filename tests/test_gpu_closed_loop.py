@@ -65,20 +65,57 @@ def test_run_test_writes_reference_artifacts(tmp_path):
     check_against_fixture(res, FIX["corridor"], 100, "corridor/run_test")
 
 
+def _agent19_actor_critic(ro, device):
+    import torch
+    a, v = np.load(os.path.join(GOLDEN, "agent_19_policy.npz")), np.load(os.path.join(GOLDEN, "agent_19_value.npz"))
+    actor = {k.replace("__", "."): torch.from_numpy(a[k]) for k in a.files}
+    critic = {k.replace("__", "."): torch.from_numpy(v[k]) for k in v.files}
+    return ro.MlpActorCritic(actor, critic, device)
+
+
 def test_rollout_collector_and_gae_kernel():
-    """(f3) device-resident rollout: GAE kernel == SB3's recursion, buffers consistent, curriculum hook works."""
+    """(f3) hand-written rollout collection (d2d_rollout_collect): the kernels write observations, unclipped actions,
+    log-probabilities, rewards, episode starts and values into the [T, N] tensors; compared with the torch float32
+    statement of the same SB3 policy (MlpActorCritic) and with SB3's GAE recursion.  Curriculum hook works."""
+    import math
     import torch
     pkg = importlib.import_module(PKG)
     ro = importlib.import_module(PKG + ".rollout")
-    env = pkg.Drone2dVecEnv(2048, seed=2, info_mode="none", mode="curriculum", scenario="stage_1")
-    pol = ro.MlpActorCritic.random_init(env.device, seed=1)
-    col = ro.RolloutCollector(env, pol, n_steps=96, seed=3).collect()
-    assert col.obs.shape == (96, 2048, 27) and col.num_timesteps == 96 * 2048
-    assert int(col.episode_starts[0].sum()) == 2048 and int(col.episode_starts[1:].sum()) > 0   # random policy: episodes end
+    T, n = 96, 2048
+    env = pkg.Drone2dVecEnv(n, seed=2, info_mode="none", mode="curriculum", scenario="stage_3")
+    pol = _agent19_actor_critic(ro, env.device)
+    col = ro.RolloutCollector(env, pol, n_steps=T, seed=3)
+    l0 = env.launch_count
+    col.collect()
+    assert env.launch_count - l0 == 2 * T + 1              # T x (policy, step) + the critic; GAE is handle-free
+    assert col.obs.shape == (T, n, 27) and col.num_timesteps == T * n
+    assert int(col.episode_starts[0].sum()) == n and int(col.episode_starts[1:].sum()) > 0
+    obs, raw = col.obs_buf, col.actions
+    # actor: the stored sample is mean + std * eps with eps ~ N(0, 1); its log-probability under the torch policy
+    mu = pol.mean(obs[:T].reshape(-1, 27)).reshape(T, n, 2)
+    eps = (raw - mu) / pol.std
+    assert abs(float(eps.mean())) < 0.01 and abs(float(eps.std()) - 1.0) < 0.01
+    logp_ref = (-0.5 * eps * eps - pol.log_std - 0.5 * math.log(2 * math.pi)).sum(-1)
+    assert float((col.log_probs - logp_ref).abs().max()) < 2e-3      # eps carries the 3e-6 error of the mean divided by std
+    # the env was stepped with the clipped sample: a second handle replays the same actions from the same seed
+    env2 = pkg.Drone2dVecEnv(n, seed=2, info_mode="none", mode="curriculum", scenario="stage_3")
+    o2 = env2.reset_device()
+    assert torch.equal(o2, obs[0])
+    for t in range(8):
+        o2, r2, d2 = env2.step_device(raw[t].clamp(-1.0, 1.0), terminal_obs=False)
+        assert torch.equal(o2, obs[t + 1]) and torch.equal(r2, col.rewards[t]) and torch.equal(d2, col.dones[t + 1])
+    env2.close()
+    # critic: one launch over all T + 1 observations vs the torch value tower
+    v_ref = pol.value(obs.reshape(-1, 27)).reshape(T + 1, n)
+    assert float((col.values_buf - v_ref).abs().max()) <= 2e-5 * max(1.0, float(v_ref.abs().max()))
     a_ref, r_ref = ro.gae_reference(col.rewards.cpu().numpy(), col.values.cpu().numpy(), col.episode_starts.cpu().numpy(),
-                                    pol.value(col._last_obs).cpu().numpy(), col._last_starts.cpu().numpy())
+                                    col.last_values.cpu().numpy(), col.last_dones.cpu().numpy())
     np.testing.assert_allclose(col.advantages.cpu().numpy(), a_ref, rtol=2e-4, atol=2e-3)
     np.testing.assert_allclose(col.returns.cpu().numpy(), r_ref, rtol=2e-4, atol=2e-3)
+    # a second rollout continues where the first one stopped
+    last = col.last_obs.clone()
+    col.collect()
+    assert torch.equal(col.obs_buf[0], last) and col.num_timesteps == 2 * T * n
     # curriculum scheduler: switch to stage_5 by training progress; new episodes get obstacles
     env.set_stage(sim_num=2_500_000)
     assert env.cfg.stage == 5

@@ -90,3 +90,49 @@ def test_inlane_fallback_is_used_when_episodes_are_shorter_than_the_prefetch_pip
     s = env.episode_stats()
     assert s["episodes"] == 20 * 4096 and s["inlane_resets"] >= 18 * 4096
     env.close()
+
+
+def test_full_size_strided_oracle_check():
+    """Parity against the oracle AT the full batch size: 65 536 stage_5 envs in steady state, every 64th env (1024
+    of them) is followed by the CPU oracle for single steps from the device's own state and tables."""
+    import ctypes as C
+    import torch
+    import oracle
+    from parity_util import blob_to_states, oracle_config_from, tables_to_structs, TOL_STATE_STEP, TOL_OBS_CORE, TOL_U
+    pkg = importlib.import_module(PKG)
+    env = pkg.Drone2dVecEnv(N, seed=9, info_mode="full", mode="curriculum", scenario="stage_5")
+    cfg = oracle_config_from(env)
+    env.reset_device()
+    for _ in range(150):
+        env.step_device(None)
+    idx = np.arange(0, N, 64)
+    rng = np.random.RandomState(3)
+    checked = flags = nearest = 0
+    worst = dict(state=0.0, obs=0.0, u=0.0, reward=0.0)
+    for rnd in range(3):
+        blob = env.get_state()
+        tabs = env.get_tables()
+        states = blob_to_states(blob[idx])
+        paths, obsts = tables_to_structs(tabs, env.cfg.n_wps, idx)
+        actions = rng.uniform(-1, 1, (N, 2)).astype(np.float32)
+        env.step_device(torch.from_numpy(actions).to(env.device))
+        g_obs, g_info, g_done = env.obs64[idx].cpu().numpy(), env.info[idx].cpu().numpy(), env.dones[idx].cpu().numpy()
+        after = env.get_state()[idx]
+        for k, i in enumerate(idx):
+            out = oracle.env_step(states[k], paths[i], obsts[i], cfg, actions[i, 0], actions[i, 1])
+            checked += 1
+            bits = out.end_collision | 2 * out.end_reached | 4 * out.end_time | 8 * out.end_alpha
+            flags += int(bool(out.done) != bool(g_done[k]) or bits != int(g_info[k, 11]))
+            near = [(int(g_info[k, 14]) >> (8 * j)) & 255 for j in range(3)]
+            nearest += int([-1 if v == 255 else v for v in near] != list(out.near_idx[:]))
+            worst["obs"] = max(worst["obs"], np.abs(g_obs[k, :19] - np.array(out.obs[:19])).max())
+            worst["u"] = max(worst["u"], abs(g_info[k, 12] - out.u_star))
+            worst["reward"] = max(worst["reward"], abs(g_info[k, 0] - out.reward))
+            if not out.done:
+                s = states[k]
+                ob = np.array([[b.px, b.py, b.vx, b.vy, b.a, b.w] for b in s.body]).ravel()
+                worst["state"] = max(worst["state"], np.abs(after[k, :18] - ob).max())
+    env.close()
+    assert checked == 3 * len(idx) and flags == 0 and nearest == 0, (checked, flags, nearest)
+    assert worst["state"] <= TOL_STATE_STEP and worst["obs"] <= TOL_OBS_CORE and worst["u"] <= TOL_U, worst
+    assert worst["reward"] <= 1e-6 + 10 * worst["u"], worst

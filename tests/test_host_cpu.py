@@ -153,7 +153,7 @@ def test_policy_weight_image_layout_and_split():
     w = [np.ascontiguousarray(z[k], dtype=np.float32) for k in keys]
     L = _lib.load()
     n = L.d2d_policy_weights_bytes()
-    assert n == 4 * (2 * 64 * 32 + 2 * 64 * 64 + 64 + 128 + 2 + 2) and n % 16 == 0
+    assert n == 4 * (2 * 64 * 32 + 2 * 64 * 64 + 64 + 128 + 2 + 2 + 2 + 2) and n % 16 == 0   # ..., b2, std, log_std, padding
     img = np.zeros(n // 4, dtype=np.float32)
     fp = lambda a: a.ctypes.data_as(C.c_void_p)
     _lib.check(L.d2d_policy_pack(*[fp(a) for a in w], fp(img)))
@@ -178,3 +178,4 @@ def test_policy_weight_image_layout_and_split():
     assert sorted(set(idx(j, k, 64) for j in range(64) for k in range(64))) == list(range(4096))   # a permutation
     assert np.array_equal(tail[:64], w[3]) and np.array_equal(tail[64:192], w[4].ravel())
     assert np.array_equal(tail[192:194], w[5]) and np.allclose(tail[194:196], np.exp(w[6]), rtol=1e-6)
+    assert np.array_equal(tail[196:198], w[6]) and not tail[198:].any()
