@@ -40,7 +40,7 @@ UNIT = "env-steps/s"
 # 401 + 256 = 657 B for the shared-table scenarios.
 ALGO_BYTES_STAGE5 = 796.0
 ALGO_BYTES_SCENARIO = 657.0
-MIN_TIMED_S = 0.5
+MIN_TIMED_S = float(os.environ.get("D2D_BENCH_MIN_S", "0.5"))    # lowered only for profiler runs (ncu replays every launch)
 ACTION_RING = 256
 SWEEP_SCENARIOS = ("S_corridor", "S_parallel", "perpendicular", "impossible")
 AGENT = os.path.join(REPO, "tests", "golden", "agent_19_policy.npz")

@@ -1132,18 +1132,20 @@ int d2d_policy_pack(const float *w0, const float *b0, const float *w1, const flo
     if (!w0 || !b0 || !w1 || !b1 || !w2 || !b2 || !log_std || !packed_host) return fail(D2D_EINVAL, "NULL argument");
     D2dPolicyImage *p = (D2dPolicyImage *)packed_host;
     memset(p, 0, sizeof *p);
+    // x = hi + lo, hi = fp16(x) (round to nearest even), lo = fp16(x - hi): 22 significant bits together
+    auto split = [](float v, __half &hi, __half &lo) {
+        hi = __float2half_rn(v);
+        lo = __float2half_rn(v - __half2float(hi));
+    };
     for (int j = 0; j < D2D_POL_H; j++) {
         for (int k = 0; k < D2D_POL_K0; k++) {           // 27 weights, the bias (matched by x[27] = 1), zero padding
             const float v = k < 27 ? w0[j * 27 + k] : (k == 27 ? b0[j] : 0.0f);
             const int o = d2d_umma_idx(j, k, D2D_POL_H);
-            p->w0_hi[o] = d2d_tf32_hi(v);
-            p->w0_lo[o] = v - p->w0_hi[o];
+            split(v, p->w0_hi[o], p->w0_lo[o]);
         }
         for (int k = 0; k < D2D_POL_K1; k++) {
-            const float v = w1[j * D2D_POL_K1 + k];
             const int o = d2d_umma_idx(j, k, D2D_POL_H);
-            p->w1_hi[o] = d2d_tf32_hi(v);
-            p->w1_lo[o] = v - p->w1_hi[o];
+            split(w1[j * D2D_POL_K1 + k], p->w1_hi[o], p->w1_lo[o]);
         }
         p->b1[j] = b1[j];
     }
@@ -1158,11 +1160,12 @@ static int launch_policy(d2d_env *e, const void *packed_weights_dev, const float
                          int stochastic, uint64_t policy_step, void *stream)
 {
     if (e->policy_grid_cap == 0) {
-        // persistent CTAs, two per SM (shared memory: 115.6 KB each; TMEM: 128 of 512 columns each)
+        // persistent CTAs, four per SM (shared memory: 49 KB each; TMEM: 128 of 512 columns each)
         CUDA_TRY(cudaFuncSetAttribute(d2d_policy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(D2dPolicySmem)));
+        CUDA_TRY(cudaFuncSetAttribute(d2d_policy_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         int sms = 0;
         CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, e->device));
-        e->policy_grid_cap = 2 * sms;
+        e->policy_grid_cap = D2D_POL_CTAS_PER_SM * sms;
     }
     const int64_t tiles = (n_rows + D2D_POL_TILE - 1) / D2D_POL_TILE;
     const int grid = (int)(tiles < e->policy_grid_cap ? tiles : e->policy_grid_cap);

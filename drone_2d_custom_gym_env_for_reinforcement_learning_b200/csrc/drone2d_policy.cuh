@@ -6,57 +6,48 @@
 //   (seed, global env id, policy step), or eps = 0.
 // This is the one GEMM-shaped piece of the path: [N envs x 27] x [27 x 64] and [N x 64] x [64 x 64].
 //
-// One CTA = one tile of 128 environments (M = 128 = the TMEM lane count), persistent over tiles:
-//   * both weight matrices live in shared memory for the CTA's lifetime, already in the tcgen05
-//     K-major / no-swizzle core-matrix layout (8 rows x 16 bytes per core matrix), packed on the host;
-//   * layer k: one elected thread issues tcgen05.mma.kind::tf32 (M128 N64 K8) over the K extent,
-//     accumulating in TMEM (64 float32 columns per layer), tcgen05.commit -> mbarrier;
-//   * each thread then owns one environment: tcgen05.ld of its TMEM lane (64 pre-activations),
-//     tanh, and either the next layer's A operand written back to shared memory or the 2-wide
-//     output layer + Gaussian noise + clip in registers.
-// float32 fidelity: every operand is split x = hi + lo with hi exactly representable in tf32
-// (round-to-nearest on the 13 dropped bits) and three products hi*hi + hi*lo + lo*hi are accumulated
-// ("3xTF32"); the result agrees with a float32 FMA chain to ~1e-6 (tests: 2e-5 against torch).
-// The first layer's bias is folded into the GEMM (x[27] = 1, W0[:, 27] = b0).
+// One CTA = one tile of 128 environments at a time (M = 128 = the TMEM lane count):
+//   * the weight matrices sit in shared memory in the tcgen05 K-major / no-swizzle core-matrix layout
+//     (8 rows x 16 bytes per core matrix), packed on the host and brought in by bulk copies of the TMA unit;
+//   * layer k: one elected thread issues tcgen05.mma.kind::f16 (M128 N64 K16) over the K extent,
+//     accumulating float32 in TMEM (64 columns per layer), tcgen05.commit -> mbarrier;
+//   * two threads per environment then tcgen05.ld their 32 columns (16 at a time), apply tanh, and either write
+//     the next layer's A operand back to shared memory or finish the 2-wide output layer + Gaussian noise + clip.
+// float32 fidelity: every operand is split x = hi + lo with hi = fp16(x), lo = fp16(x - hi) (22 significant bits
+// together, like the tf32 split used before) and three products hi*hi + hi*lo + lo*hi are accumulated in float32;
+// the result agrees with a float32 FMA chain to ~1e-6 (tests: 2e-5 against torch).  The first layer's bias is folded
+// into the GEMM (x[27] = 1, W0[:, 27] = b0).
+// Footprint: half-precision operands need half the bytes of tf32 and half the MMAs (K = 16 per instruction); the
+// hidden activations H overwrite the region that held W0 and X (both dead by then; W0 is re-fetched per tile, 8 KB),
+// so a CTA needs 49 KB of shared memory and 128 TMEM columns: FOUR CTAs per SM, i.e. all 512 tiles of 65 536
+// environments are resident at once and the launch lasts one tile's latency chain instead of two.
 #pragma once
 #include <cstdint>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #define D2D_POL_TILE 128          // environments per CTA tile = UMMA M
 #define D2D_POL_H 64              // hidden width = UMMA N
-#define D2D_POL_K0 32             // 27 inputs + bias + 4 zero columns (K must be a multiple of 8)
+#define D2D_POL_K0 32             // 27 inputs + bias + 4 zero columns (K must be a multiple of 16)
 #define D2D_POL_K1 64
 #define D2D_STREAM_POLICY 0x504F4C49u   // 'POLI'
 
-// float index of element (r, k) of an [R rows][K] operand in the UMMA K-major no-swizzle layout:
-// core matrix = 8 rows x 4 floats (128 contiguous bytes), core matrices ordered row-group-fastest.
-__host__ __device__ inline int d2d_umma_idx(int r, int k, int R) { return ((k >> 2) * (R >> 3) + (r >> 3)) * 32 + (r & 7) * 4 + (k & 3); }
+// half index of element (r, k) of an [R rows][K] operand in the UMMA K-major no-swizzle layout:
+// core matrix = 8 rows x 8 halfs (128 contiguous bytes), core matrices ordered row-group-fastest.
+__host__ __device__ inline int d2d_umma_idx(int r, int k, int R) { return ((k >> 3) * (R >> 3) + (r >> 3)) * 64 + (r & 7) * 8 + (k & 7); }
 
-// Host-built image, copied verbatim into shared memory.
+// Host-built image, copied verbatim into shared memory.  The first-layer weights come LAST: together with the X
+// operand behind them they form the region the hidden activations overwrite (see D2dPolicySmem).
 struct D2dPolicyImage {
-    float w0_hi[D2D_POL_H * D2D_POL_K0], w0_lo[D2D_POL_H * D2D_POL_K0];
-    float w1_hi[D2D_POL_H * D2D_POL_K1], w1_lo[D2D_POL_H * D2D_POL_K1];
+    __half w1_hi[D2D_POL_H * D2D_POL_K1], w1_lo[D2D_POL_H * D2D_POL_K1];
     float b1[D2D_POL_H];
     float w2[2 * D2D_POL_H];
     float b2[2];
     float std[2];
     float log_std[2];
-    float pad_[2];
+    float pad_[26];               // the operand regions below start on a 128-byte (core-matrix) boundary
+    __half w0_hi[D2D_POL_H * D2D_POL_K0], w0_lo[D2D_POL_H * D2D_POL_K0];
 };
-
-__host__ __device__ inline float d2d_tf32_hi(float x)
-{
-#ifdef __CUDA_ARCH__
-    return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
-#else
-    uint32_t b;
-    memcpy(&b, &x, 4);
-    b = (b + 0x1000u) & 0xffffe000u;
-    float r;
-    memcpy(&r, &b, 4);
-    return r;
-#endif
-}
 
 namespace pol {
 
@@ -70,19 +61,20 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_b
            ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
 }
 
-// instruction descriptor (cute::UMMA::InstrDescriptor): D = f32, A = B = tf32, both K-major, N = 64, M = 128
+// instruction descriptor (cute::UMMA::InstrDescriptor): D = f32 (c_format 1), A = B = f16 (format 0), both K-major,
+// N = 64, M = 128
 __device__ __forceinline__ constexpr uint32_t umma_idesc()
 {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(D2D_POL_H >> 3) << 17) | ((uint32_t)(D2D_POL_TILE >> 4) << 24);
+    return (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(D2D_POL_H >> 3) << 17) | ((uint32_t)(D2D_POL_TILE >> 4) << 24);
 }
 
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t accumulate)
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t accumulate)
 {
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t"
         "}\n" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(umma_idesc()), "r"(accumulate), "r"(0u)
         : "memory");
 }
@@ -120,22 +112,34 @@ __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence:
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void async_proxy_fence() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// 32 consecutive float32 columns of this thread's TMEM lane
-__device__ __forceinline__ void tmem_ld32(uint32_t addr, float *v)
+// 16 consecutive float32 columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld16(uint32_t addr, float *v)
 {
-    uint32_t r[32];
+    uint32_t r[16];
     asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(addr));
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-    for (int j = 0; j < 32; j++) v[j] = __uint_as_float(r[j]);
+    for (int j = 0; j < 16; j++) v[j] = __uint_as_float(r[j]);
+}
+
+// x = hi + lo with hi = fp16(x), lo = fp16(x - hi): 8 consecutive K elements of one operand row = one 16-byte
+// core-matrix row of each half
+__device__ __forceinline__ void split8(const float *x, uint4 &hi, uint4 &lo)
+{
+    __half2 h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const __half a = __float2half_rn(x[2 * j]), b = __float2half_rn(x[2 * j + 1]);
+        h[j] = __halves2half2(a, b);
+        l[j] = __halves2half2(__float2half_rn(x[2 * j] - __half2float(a)), __float2half_rn(x[2 * j + 1] - __half2float(b)));
+    }
+    hi = *reinterpret_cast<uint4 *>(h);
+    lo = *reinterpret_cast<uint4 *>(l);
 }
 
 // tanh from the exponential: 1 - 2 / (exp(2|x|) + 1), ex2.approx + rcp.approx, |error| < 3e-7
@@ -149,20 +153,24 @@ __device__ __forceinline__ float tanh_fast(float x)
 
 }  // namespace pol
 
-// shared memory of one CTA: weight image, the A operand region (X hi/lo of layer 0, later H hi/lo of
-// layer 1: the two never live at the same time; its last KB also carries the partial outputs of the upper
-// column half between the last epilogue and the next tile's first), two mbarriers and the TMEM
-// base address.  115.5 KB -> two CTAs per SM.
+// shared memory of one CTA: the weight image, the X operand (hi | lo) and 8 KB more.  The hidden activations
+// H (hi | lo, 2 x 16 KB) overwrite [w0_hi .. spare]: W0 and X are dead once layer 0 has been accumulated; the last KB
+// of the region carries the partial outputs of the upper column half between the last epilogue and the next tile.
 static_assert(sizeof(D2dPolicyImage) % 16 == 0, "bulk copies move multiples of 16 bytes");
+static_assert(offsetof(D2dPolicyImage, w0_hi) % 128 == 0, "operand regions start on a core-matrix boundary");
 
 struct D2dPolicySmem {
     D2dPolicyImage w;
-    float a[2 * D2D_POL_TILE * D2D_POL_K1];       // [hi | lo], each up to 128 x 64
+    __half x[2 * D2D_POL_TILE * D2D_POL_K0];      // [hi | lo], 2 x 8 KB
+    unsigned char spare[8192];
     unsigned long long bar[3];
     uint32_t tmem_base;
 };
+static_assert(2 * D2D_POL_H * D2D_POL_K0 * 2 + 2 * D2D_POL_TILE * D2D_POL_K0 * 2 + 8192 == 2 * D2D_POL_TILE * D2D_POL_K1 * 2,
+              "W0 + X + spare is exactly the H operand (hi | lo)");
 
 #define D2D_POL_THREADS 256       // two threads per environment row: columns [0,32) and [32,64) of every layer
+#define D2D_POL_CTAS_PER_SM 4
 
 // observation elements [16*half, 16*half + 16) of one row (27 real inputs, then the bias column 1, then zeros)
 __device__ __forceinline__ void d2d_policy_fetch(const float *__restrict__ obs, int64_t n, int64_t row, int half, float *xr)
@@ -183,16 +191,16 @@ struct D2dPolicyOut {
     float *actions, *actions_raw, *log_prob, *values;
 };
 
-__global__ void __launch_bounds__(D2D_POL_THREADS, 2) d2d_policy_kernel(const D2dPolicyImage *__restrict__ image,
-                                                                        const float *__restrict__ obs, D2dPolicyOut out,
-                                                                        int64_t n, int stochastic, uint32_t seed_lo, uint32_t seed_hi,
-                                                                        int64_t env_id_base, uint64_t step_index)
+__global__ void __launch_bounds__(D2D_POL_THREADS, D2D_POL_CTAS_PER_SM)
+d2d_policy_kernel(const D2dPolicyImage *__restrict__ image, const float *__restrict__ obs, D2dPolicyOut out, int64_t n, int stochastic,
+                  uint32_t seed_lo, uint32_t seed_hi, int64_t env_id_base, uint64_t step_index)
 {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     D2dPolicySmem &S = *reinterpret_cast<D2dPolicySmem *>(smem_raw);
     const int tid = threadIdx.x, warp = tid >> 5, row = tid & (D2D_POL_TILE - 1), half = tid >> 7;
     const uint32_t bar0 = pol::smem_u32(&S.bar[0]), bar1 = pol::smem_u32(&S.bar[1]), barw = pol::smem_u32(&S.bar[2]);
     const int64_t n_tiles = (n + D2D_POL_TILE - 1) / D2D_POL_TILE;
+    constexpr uint32_t W0_BYTES = 2 * D2D_POL_H * D2D_POL_K0 * 2;
 
     asm volatile("griddepcontrol.launch_dependents;");           // the next step kernel may queue up behind us
     // ---- one-time setup: barriers, TMEM (128 columns: layer-0 and layer-1 accumulators), weights ----
@@ -201,7 +209,7 @@ __global__ void __launch_bounds__(D2D_POL_THREADS, 2) d2d_policy_kernel(const D2
         pol::mbar_init(bar1, 1);
         pol::mbar_init(barw, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        // the 49.9 KB weight image comes in as ONE bulk copy of the TMA unit, completing on barw
+        // the 25 KB weight image comes in as ONE bulk copy of the TMA unit, completing on barw
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(barw), "r"((uint32_t)sizeof(D2dPolicyImage)) : "memory");
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(pol::smem_u32(&S.w)),
                      "l"(image), "r"((uint32_t)sizeof(D2dPolicyImage)), "r"(barw)
@@ -220,103 +228,116 @@ __global__ void __launch_bounds__(D2D_POL_THREADS, 2) d2d_policy_kernel(const D2
     pol::tc_fence_before();
     __syncthreads();
     pol::tc_fence_after();
-    pol::mbar_wait(barw, 0);                     // the weight image has landed (async proxy -> async proxy: no proxy fence needed)
+    pol::mbar_wait(barw, 0);                     // the weight image has landed (every thread reads b1 / w2 / b2 / std from it)
     const uint32_t tmem = S.tmem_base;
     const uint32_t tmem_lane = tmem + ((uint32_t)((warp & 3) * 32) << 16);   // a warp reaches the 32 TMEM lanes of its quarter
 
-    float *a_hi = S.a, *a_lo = S.a + D2D_POL_TILE * D2D_POL_K1;
-    // written after layer 1 has consumed H, read before the next tile's H is produced; X (the first 16 KB of each half) never reaches it
-    float2 *part = reinterpret_cast<float2 *>(a_lo + D2D_POL_TILE * D2D_POL_K1) - D2D_POL_TILE;
-    const uint32_t a_hi_s = pol::smem_u32(a_hi);
+    unsigned char *hreg = reinterpret_cast<unsigned char *>(S.w.w0_hi);      // H operand: hi at +0, lo at +16 KB
+    unsigned char *xreg = reinterpret_cast<unsigned char *>(S.x);            // X operand: hi at +0, lo at +8 KB
+    // written after layer 1 has consumed H, read before the next tile's H is produced; neither the W0 re-fetch (first
+    // 8 KB of the region) nor the next X (the 16 KB behind it) reaches the region's last KB
+    float2 *part = reinterpret_cast<float2 *>(hreg + 2 * D2D_POL_TILE * D2D_POL_K1 * 2) - D2D_POL_TILE;
+    const uint32_t h_s = pol::smem_u32(hreg), x_s = pol::smem_u32(xreg);
     const uint32_t w0_hi_s = pol::smem_u32(S.w.w0_hi), w0_lo_s = pol::smem_u32(S.w.w0_lo);
     const uint32_t w1_hi_s = pol::smem_u32(S.w.w1_hi), w1_lo_s = pol::smem_u32(S.w.w1_lo);
     constexpr uint32_t LBO_A = (D2D_POL_TILE / 8) * 128, LBO_B = (D2D_POL_H / 8) * 128, SBO = 128;
-    constexpr uint32_t A_LO_OFF = D2D_POL_TILE * D2D_POL_K1 * 4;          // byte offset of the lo half
+    constexpr uint32_t X_LO_OFF = D2D_POL_TILE * D2D_POL_K0 * 2, H_LO_OFF = D2D_POL_TILE * D2D_POL_K1 * 2;   // bytes
+    // byte offset of this thread's row inside a K chunk (8 halfs = 16 bytes per row, 16 row groups of 128 bytes per chunk)
+    const uint32_t row_off = (uint32_t)(row >> 3) * 128 + (uint32_t)(row & 7) * 16;
 
     uint32_t phase = 0;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, phase ^= 1u) {
         const int64_t base = tile * D2D_POL_TILE;
 
-        // ---- A operand of layer 0: this thread's 16 inputs, split and laid out for the MMA ----
+        // ---- A operand of layer 0: this thread's 16 inputs = K chunks 2*half and 2*half + 1 of its row ----
 #pragma unroll
-        for (int c = 0; c < 4; c++) {
-            float4 h, l;
-            h.x = d2d_tf32_hi(xr[4 * c]); h.y = d2d_tf32_hi(xr[4 * c + 1]); h.z = d2d_tf32_hi(xr[4 * c + 2]); h.w = d2d_tf32_hi(xr[4 * c + 3]);
-            l.x = xr[4 * c] - h.x; l.y = xr[4 * c + 1] - h.y; l.z = xr[4 * c + 2] - h.z; l.w = xr[4 * c + 3] - h.w;
-            const int o = d2d_umma_idx(row, half * 16 + 4 * c, D2D_POL_TILE);
-            *reinterpret_cast<float4 *>(&a_hi[o]) = h;
-            *reinterpret_cast<float4 *>(&a_lo[o]) = l;
+        for (int c = 0; c < 2; c++) {
+            uint4 hi, lo;
+            pol::split8(&xr[8 * c], hi, lo);
+            const uint32_t o = (uint32_t)(2 * half + c) * LBO_A + row_off;
+            *reinterpret_cast<uint4 *>(xreg + o) = hi;
+            *reinterpret_cast<uint4 *>(xreg + X_LO_OFF + o) = lo;
         }
         pol::async_proxy_fence();
         pol::tc_fence_before();
         __syncthreads();
 
-        // ---- layer 0: D0[128 x 64] = X[128 x 32] * W0^T, 4 K-steps x 3 split products ----
+        // ---- layer 0: D0[128 x 64] = X[128 x 32] * W0^T, 2 K-steps x 3 split products ----
         if (tid == 0) {
+            pol::mbar_wait(barw, phase);         // the weight image (first tile) / the re-fetched W0 has landed
             pol::tc_fence_after();
 #pragma unroll
-            for (int ks = 0; ks < D2D_POL_K0 / 8; ks++) {
-                const uint64_t ah = pol::umma_desc(a_hi_s + ks * 2 * LBO_A, LBO_A, SBO);
-                const uint64_t al = pol::umma_desc(a_hi_s + A_LO_OFF + ks * 2 * LBO_A, LBO_A, SBO);
+            for (int ks = 0; ks < D2D_POL_K0 / 16; ks++) {
+                const uint64_t ah = pol::umma_desc(x_s + ks * 2 * LBO_A, LBO_A, SBO);
+                const uint64_t al = pol::umma_desc(x_s + X_LO_OFF + ks * 2 * LBO_A, LBO_A, SBO);
                 const uint64_t bh = pol::umma_desc(w0_hi_s + ks * 2 * LBO_B, LBO_B, SBO);
                 const uint64_t bl = pol::umma_desc(w0_lo_s + ks * 2 * LBO_B, LBO_B, SBO);
-                pol::umma_tf32(tmem, ah, bh, ks > 0);
-                pol::umma_tf32(tmem, ah, bl, 1);
-                pol::umma_tf32(tmem, al, bh, 1);
+                pol::umma_f16(tmem, ah, bh, ks > 0);
+                pol::umma_f16(tmem, ah, bl, 1);
+                pol::umma_f16(tmem, al, bh, 1);
             }
             pol::umma_commit(bar0);
         }
         // the next tile's observations travel while the tensor core and the epilogues work
-        if (tile + gridDim.x < n_tiles) d2d_policy_fetch(obs, n, (tile + gridDim.x) * D2D_POL_TILE + row, half, xr);
+        const bool more = tile + gridDim.x < n_tiles;
+        if (more) d2d_policy_fetch(obs, n, (tile + gridDim.x) * D2D_POL_TILE + row, half, xr);
         pol::mbar_wait(bar0, phase);
         pol::tc_fence_after();
 
-        // ---- hidden layer 0 activations -> A operand of layer 1 (this thread's row, its 32 columns) ----
-        {
-            float v[32];
-            pol::tmem_ld32(tmem_lane + half * 32, v);
+        // ---- hidden layer 0 activations -> A operand of layer 1 (this thread's row, its 32 columns), over W0 and X ----
 #pragma unroll
-            for (int c = 0; c < 8; c++) {
-                float4 h, l;
-                const float t0 = pol::tanh_fast(v[4 * c]), t1 = pol::tanh_fast(v[4 * c + 1]);
-                const float t2 = pol::tanh_fast(v[4 * c + 2]), t3 = pol::tanh_fast(v[4 * c + 3]);
-                h.x = d2d_tf32_hi(t0); h.y = d2d_tf32_hi(t1); h.z = d2d_tf32_hi(t2); h.w = d2d_tf32_hi(t3);
-                l.x = t0 - h.x; l.y = t1 - h.y; l.z = t2 - h.z; l.w = t3 - h.w;
-                const int o = d2d_umma_idx(row, half * 32 + 4 * c, D2D_POL_TILE);
-                *reinterpret_cast<float4 *>(&a_hi[o]) = h;
-                *reinterpret_cast<float4 *>(&a_lo[o]) = l;
+        for (int q = 0; q < 2; q++) {
+            float v[16];
+            pol::tmem_ld16(tmem_lane + half * 32 + q * 16, v);
+#pragma unroll
+            for (int j = 0; j < 16; j++) v[j] = pol::tanh_fast(v[j]);
+#pragma unroll
+            for (int c = 0; c < 2; c++) {
+                uint4 hi, lo;
+                pol::split8(&v[8 * c], hi, lo);
+                const uint32_t o = (uint32_t)(4 * half + 2 * q + c) * LBO_A + row_off;
+                *reinterpret_cast<uint4 *>(hreg + o) = hi;
+                *reinterpret_cast<uint4 *>(hreg + H_LO_OFF + o) = lo;
             }
         }
         pol::async_proxy_fence();
         pol::tc_fence_before();
         __syncthreads();
 
-        // ---- layer 1: D1[128 x 64] = H[128 x 64] * W1^T, 8 K-steps x 3 split products ----
+        // ---- layer 1: D1[128 x 64] = H[128 x 64] * W1^T, 4 K-steps x 3 split products ----
         if (tid == 0) {
             pol::tc_fence_after();
 #pragma unroll
-            for (int ks = 0; ks < D2D_POL_K1 / 8; ks++) {
-                const uint64_t ah = pol::umma_desc(a_hi_s + ks * 2 * LBO_A, LBO_A, SBO);
-                const uint64_t al = pol::umma_desc(a_hi_s + A_LO_OFF + ks * 2 * LBO_A, LBO_A, SBO);
+            for (int ks = 0; ks < D2D_POL_K1 / 16; ks++) {
+                const uint64_t ah = pol::umma_desc(h_s + ks * 2 * LBO_A, LBO_A, SBO);
+                const uint64_t al = pol::umma_desc(h_s + H_LO_OFF + ks * 2 * LBO_A, LBO_A, SBO);
                 const uint64_t bh = pol::umma_desc(w1_hi_s + ks * 2 * LBO_B, LBO_B, SBO);
                 const uint64_t bl = pol::umma_desc(w1_lo_s + ks * 2 * LBO_B, LBO_B, SBO);
-                pol::umma_tf32(tmem + D2D_POL_H, ah, bh, ks > 0);
-                pol::umma_tf32(tmem + D2D_POL_H, ah, bl, 1);
-                pol::umma_tf32(tmem + D2D_POL_H, al, bh, 1);
+                pol::umma_f16(tmem + D2D_POL_H, ah, bh, ks > 0);
+                pol::umma_f16(tmem + D2D_POL_H, ah, bl, 1);
+                pol::umma_f16(tmem + D2D_POL_H, al, bh, 1);
             }
             pol::umma_commit(bar1);
         }
         pol::mbar_wait(bar1, phase);
         pol::tc_fence_after();
+        if (tid == 0 && more) {
+            // H is dead: bring W0 back for the next tile while the output layer runs (8 KB, completes on barw)
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(barw), "r"(W0_BYTES) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(w0_hi_s),
+                         "l"(image->w0_hi), "r"(W0_BYTES), "r"(barw)
+                         : "memory");
+        }
 
         // ---- output layer over this thread's 32 columns; the two halves of a row meet in shared memory ----
         float mu0 = 0.0f, mu1 = 0.0f;
-        {
-            float v[32];
-            pol::tmem_ld32(tmem_lane + D2D_POL_H + half * 32, v);
 #pragma unroll
-            for (int j = 0; j < 32; j++) {
-                const int jj = half * 32 + j;
+        for (int q = 0; q < 2; q++) {
+            float v[16];
+            pol::tmem_ld16(tmem_lane + D2D_POL_H + half * 32 + q * 16, v);
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
+                const int jj = half * 32 + q * 16 + j;
                 const float h2 = pol::tanh_fast(v[j] + S.w.b1[jj]);
                 mu0 = fmaf(S.w.w2[jj], h2, mu0);
                 mu1 = fmaf(S.w.w2[D2D_POL_H + jj], h2, mu1);
@@ -324,7 +345,7 @@ __global__ void __launch_bounds__(D2D_POL_THREADS, 2) d2d_policy_kernel(const D2
         }
         if (half) part[row] = make_float2(mu0, mu1);
         pol::tc_fence_before();
-        __syncthreads();                         // partial sums visible; TMEM and the A region are free for the next tile
+        __syncthreads();                         // partial sums visible; TMEM and the operand regions are free for the next tile
         if (!half && base + row < n) {
             const float2 other = part[row];
             mu0 += other.x + S.w.b2[0];
@@ -354,6 +375,8 @@ __global__ void __launch_bounds__(D2D_POL_THREADS, 2) d2d_policy_kernel(const D2
                     make_float2(fminf(fmaxf(mu0, -1.0f), 1.0f), fminf(fmaxf(mu1, -1.0f), 1.0f));
             }
         }
+        // `part` is read above by threads that then run ahead into the next tile; nobody writes the region's last KB
+        // before the next tile's second __syncthreads (H of the next tile), which these readers also pass first
     }
 
     __syncthreads();

@@ -306,21 +306,26 @@ class Drone2dVecEnv:
                 "flight_path": [],                 # env:612; positions are not recorded on the device
                 "episode": {"r": float(r[10]), "l": int(r[7])}}
 
-    _ROW_KEYS = INFO_KEYS + ("APE", "total_reward")          # info-tap columns 0..10
+    _DONE_KEYS = ("reward", "collision_avoidance_reward", "path_adherence", "path_progression", "collision_reward",
+                  "reach_end_reward", "agressive_alpha_reward", "dist_closest_obs", "APE", "total_reward", "env_steps",
+                  "n_collisions", "n_successful_runs", "n_failed_runs")
 
     def _done_infos(self, rows):
-        """Info dicts of the envs that finished this step (rows: their info-tap rows), built from Python floats."""
+        """Info dicts of the envs that finished this step (rows: their info-tap rows [m, 16]).  The integer keys are
+        derived for all rows at once; each dict is then one dict(zip(...)) over Python scalars."""
+        bits = rows[:, 11].astype(np.int64)
+        steps = rows[:, 7].astype(np.int64).tolist()
+        cols = [rows[:, j].tolist() for j in (0, 1, 2, 3, 4, 5, 6, 8, 9, 10)]
+        cols.append(steps)
+        cols.append((((bits & 1) != 0) & ((bits & 14) == 0)).astype(np.int64).tolist())      # env:595-610 overwrite order
+        cols.append(((bits & 2) != 0).astype(np.int64).tolist())
+        cols.append(((bits & 13) != 0).astype(np.int64).tolist())
+        keys = self._DONE_KEYS
         out = []
-        keys = self._ROW_KEYS
-        for r in rows.tolist():
-            bits, steps = int(r[11]), int(r[7])
-            d = dict(zip(keys, r))
-            d["env_steps"] = steps
-            d["n_collisions"] = int(bool(bits & 1) and not (bits & 14))      # env:595-610 overwrite order
-            d["n_successful_runs"] = int(bool(bits & 2))
-            d["n_failed_runs"] = int(bool(bits & 13))
+        for vals in zip(*cols):
+            d = dict(zip(keys, vals))
             d["flight_path"] = []
-            d["episode"] = {"r": r[10], "l": steps}
+            d["episode"] = {"r": vals[9], "l": vals[10]}
             out.append(d)
         return out
 
@@ -365,7 +370,28 @@ class Drone2dVecEnv:
             pass
 
     def seed(self, seed=None):
-        """The reset stream is keyed at construction; returns the seeds SB3 expects."""
+        """SB3 VecEnv.seed: re-key the counter-based reset stream (takes effect at the next reset(); the handle is
+        rebuilt on the same state tensor, taps / scenario / stage / flight-path ring are registered again) and return
+        the per-env seeds (global env i draws from stream (seed, env_id_base + i, episode))."""
+        if seed is not None and int(seed) != self.seed_value:
+            self.seed_value = int(seed)
+            torch.cuda.synchronize(self.device)
+            self._L.d2d_destroy(self._h)
+            self._h = C.c_void_p()
+            dev = self.device
+            _lib.check(self._L.d2d_create(C.byref(self.cfg), self.num_envs, self.env_id_base, self.seed_value & (2 ** 64 - 1),
+                                          dev.index if dev.index is not None else torch.cuda.current_device(),
+                                          self.state.data_ptr(), self.state.numel(), C.byref(self._h)))
+            if self.info is not None:
+                _lib.check(self._L.d2d_set_taps(self._h, self.obs64.data_ptr() if self.obs64 is not None else None, self.info.data_ptr()))
+                _lib.check(self._L.d2d_set_info_done_only(self._h, 1 if self.info_mode == "episode" else 0))
+            if self.cfg.mode == _lib.MODE_TEST:
+                sc = self.scenario
+                self.set_scenario(sc["wps"], sc["us"], sc["xparams"], sc["yparams"], sc["obstacles"])
+            else:
+                _lib.check(self._L.d2d_set_stage(self._h, int(self.cfg.stage), float(self.cfg.stage_spawn_chance)))
+            if self.path_ring is not None:
+                _lib.check(self._L.d2d_set_flight_path_ring(self._h, self.path_ring.data_ptr(), int(self.path_ring.shape[0])))
         return [self.seed_value + self.env_id_base + i for i in range(self.num_envs)]
 
     def get_attr(self, attr_name, indices=None):

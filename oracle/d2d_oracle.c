@@ -24,8 +24,9 @@
 #endif
 
 /* pymunk Space.damping: never set by the reference (default 1.0).  env:376-380 assigns a plain Python
- * attribute `body.damping = 0.9`, which Chipmunk never sees; tests/test_physics_pin.py checks this
- * against genuine pymunk trajectories by rebuilding the oracle with -DD2O_SPACE_DAMPING=0.9. */
+ * attribute `body.damping = 0.9`, which Chipmunk never sees; tests/test_reference_trajectories_cpu.py
+ * (test_no_damping_in_the_genuine_runs) and tests/test_inverse_dynamics_cpu.py check this against genuine pymunk
+ * trajectories by rebuilding the oracle with -DD2O_SPACE_DAMPING=0.9. */
 /* Further compile-time variants of the solver, used ONLY by the inverse-dynamics discriminator
  * (tests/test_inverse_dynamics_cpu.py) to show that the genuine pymunk trajectories reject them:
  *   -DD2O_NO_WARM_START          cached impulses are not re-applied at the start of a step

@@ -9,17 +9,18 @@
  *              tables -- checked against tests/golden/ (vectors produced by the
  *              reference's own predef_path.py / test_scenarios.py, see
  *              tests/golden/make_golden.py).
- *   UNPINNED : the rigid-body step.  The reference delegates it to pymunk
- *              (Chipmunk2D 7.0.x, un-vendored, un-pinned; neither importable nor
- *              on disk here).  d2o_space_step restates Chipmunk's published
- *              cpSpaceStep / cpBodyUpdatePosition / cpBodyUpdateVelocity /
- *              cpPivotJoint algorithm for this world (3 bodies, 6 pivots,
- *              10 iterations) and is anchored only on the reference's call
- *              sites (Drone.py:9-95, drone_2d_env.py:184-191,403-406), on
- *              closed-loop statistics (tests/golden/closed_loop.json) and on the
- *              genuine pymunk trajectories of the reference's evaluation runs
- *              (tests/golden/reference_trajectories.npz: implied-thrust
- *              distribution; tests/test_reference_trajectories_cpu.py).
+ *   pinned at step level on GENUINE pymunk output: the rigid-body step.  The reference delegates it to pymunk
+ *              (Chipmunk2D 7.0.x, un-vendored, un-pinned; neither importable nor on disk here, nor on the GPU
+ *              box -- profiles/r02_box_probe.txt).  d2o_space_step restates Chipmunk's published cpSpaceStep /
+ *              cpBodyUpdatePosition / cpBodyUpdateVelocity / cpPivotJoint algorithm for this world (3 bodies,
+ *              6 pivots, 10 iterations), anchored on the reference's call sites (Drone.py:9-95,
+ *              drone_2d_env.py:184-191,403-406).  It is checked against the frame positions the reference's own
+ *              evaluation runs recorded after every space.step (700 episodes, 395 k steps): motor commands inside
+ *              the action Box exist under which d2o_space_step reproduces every recorded velocity to ~1e-8 px/s
+ *              (oracle/inverse_dynamics.py, tests/test_inverse_dynamics_cpu.py), while 9 or 11 solver
+ *              iterations, no warm start, another joint order, another integration order, damping, a 2.5 %
+ *              heavier motor or 0.1 % more gravity leave residuals 4-7 orders of magnitude larger.  What this
+ *              cannot see: the angle and the motor bodies are not recorded, only the frame position is.
  *   pinned on genuine step() outputs (same fixtures): APE, termination step
  *              and reason, total reward of 70 reference episodes replayed
  *              through d2o_after_physics.

@@ -86,7 +86,12 @@ class Episode:
         """Returns dict(actions [m,2] committed (snapped), raw [m,2] as estimated, residual [m] = max |v_model - v_obs|
         of each committed step under the committed actions, alpha0)."""
         n = self.n if max_steps is None else min(self.n, max_steps)
-        alpha0 = float(self.theta_obs[0])
+        # Spawn angle = direction of the first thrust.  With both motor commands at -1 the thrust is exactly zero and so
+        # is the torque: the drone falls without turning until the first step with thrust, whose direction is the angle.
+        lit = np.flatnonzero(self.mag > 1.0)
+        j0 = int(lit[0]) if len(lit) else 0
+        alpha0 = float(self.theta_obs[j0])
+        self.alpha0_exact = bool(j0 == 0 or self.mag[:j0].max() < 1e-6)
         state = B.spawn(self.xy[0, 0], self.xy[0, 1], alpha0, self.cfg)   # exact state at the start of the window
         k0 = 0                                                          # first step of the window
         x = np.zeros((0, 2))                                            # current estimate of the window's actions
@@ -138,7 +143,8 @@ class Episode:
                 v = self.advance(state, a)
                 committed.append(a); raw.append(a_raw); resid.append(float(np.abs(v - self.vobs[k0]).max()))
                 x = x[1:]; k0 += 1
-        return {"actions": np.array(committed), "raw": np.array(raw), "residual": np.array(resid), "alpha0": alpha0}
+        return {"actions": np.array(committed), "raw": np.array(raw), "residual": np.array(resid), "alpha0": alpha0,
+                "alpha0_exact": self.alpha0_exact}
 
 
 def summarize(rec, tail=24):

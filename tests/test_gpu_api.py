@@ -203,3 +203,18 @@ def test_flight_path_in_infos_when_render_path_is_set():
         _, _, dones, infos = env.step(np.zeros((8, 2), np.float32))
     assert dones.all() and infos[0]["flight_path"] == [] and env.path_ring is None
     env.close()
+
+
+def test_seed_rekeys_the_reset_stream():
+    """SB3 VecEnv.seed(seed): the next reset draws from the new stream; the same seed gives the same episodes."""
+    pkg = importlib.import_module(PKG)
+    env = pkg.Drone2dVecEnv(64, seed=1, mode="curriculum", scenario="stage_5")
+    a = env.reset().copy()
+    assert env.seed(7) == [7 + i for i in range(64)]
+    b = env.reset().copy()
+    env.seed(1)
+    c = env.reset().copy()
+    assert not np.array_equal(a, b) and np.array_equal(a, c)
+    obs, rew, dones, infos = env.step(np.zeros((64, 2), np.float32))       # the rebuilt handle steps and fills infos
+    assert obs.shape == (64, 27) and np.isfinite(obs).all()
+    env.close()

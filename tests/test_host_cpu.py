@@ -143,9 +143,9 @@ def test_vec_env_fails_loudly_without_cuda():
 
 def test_policy_weight_image_layout_and_split():
     """d2d_policy_pack (host code of the library): the image the tcgen05 kernel copies into shared memory.
-    Every operand element sits at its UMMA K-major core-matrix position, hi is exactly representable in
-    tf32 (13 low mantissa bits zero), hi + lo reproduces the float32 weight exactly, the first layer's bias is
-    column 27, columns 28..31 are zero."""
+    Every operand element sits at its UMMA K-major core-matrix position (8 rows x 8 halfs), hi = fp16(w) and
+    hi + lo reproduces the float32 weight to 22 bits, the first layer's bias is column 27, columns 28..31 are zero;
+    the first-layer weights come last (the kernel overwrites them with the hidden activations)."""
     import ctypes as C
     z = np.load(os.path.join(GOLDEN, "agent_19_policy.npz"))
     keys = ("mlp_extractor__policy_net__0__weight", "mlp_extractor__policy_net__0__bias", "mlp_extractor__policy_net__2__weight",
@@ -153,28 +153,30 @@ def test_policy_weight_image_layout_and_split():
     w = [np.ascontiguousarray(z[k], dtype=np.float32) for k in keys]
     L = _lib.load()
     n = L.d2d_policy_weights_bytes()
-    assert n == 4 * (2 * 64 * 32 + 2 * 64 * 64 + 64 + 128 + 2 + 2 + 2 + 2) and n % 16 == 0   # ..., b2, std, log_std, padding
-    img = np.zeros(n // 4, dtype=np.float32)
+    small = 4 * (64 + 128 + 2 + 2 + 2 + 26)                       # b1, w2, b2, std, log_std, padding to 128 bytes
+    assert n == 2 * 2 * 64 * 64 + small + 2 * 2 * 64 * 32 and n % 16 == 0 and (2 * 2 * 64 * 64 + small) % 128 == 0
+    img = np.zeros(n, dtype=np.uint8)
     fp = lambda a: a.ctypes.data_as(C.c_void_p)
     _lib.check(L.d2d_policy_pack(*[fp(a) for a in w], fp(img)))
 
-    def idx(r, k, R):                                   # d2d_umma_idx
-        return ((k >> 2) * (R >> 3) + (r >> 3)) * 32 + (r & 7) * 4 + (k & 3)
+    def idx(r, k, R):                                   # d2d_umma_idx (halfs)
+        return ((k >> 3) * (R >> 3) + (r >> 3)) * 64 + (r & 7) * 8 + (k & 7)
 
-    w0_hi, w0_lo = img[0:2048], img[2048:4096]
-    w1_hi, w1_lo = img[4096:8192], img[8192:12288]
-    tail = img[12288:]
-    for hi in (w0_hi, w1_hi):
-        assert not (hi.view(np.uint32) & 0x1FFF).any()
+    w1_hi, w1_lo = img[0:8192].view(np.float16), img[8192:16384].view(np.float16)
+    tail = img[16384:16384 + small].view(np.float32)
+    w0 = img[16384 + small:]
+    w0_hi, w0_lo = w0[0:4096].view(np.float16), w0[4096:8192].view(np.float16)
     full0 = np.zeros((64, 32), np.float32)
     full0[:, :27], full0[:, 27] = w[0], w[1]
     for j in range(64):
         for k in range(32):
             o = idx(j, k, 64)
-            assert w0_hi[o] + w0_lo[o] == full0[j, k] and abs(w0_lo[o]) <= abs(full0[j, k]) * 2.0 ** -11 + 1e-45
+            assert w0_hi[o] == np.float16(full0[j, k])
+            assert abs(float(w0_hi[o]) + float(w0_lo[o]) - float(full0[j, k])) <= abs(float(full0[j, k])) * 2.0 ** -21 + 6e-8
         for k in range(64):
             o = idx(j, k, 64)
-            assert w1_hi[o] + w1_lo[o] == w[2][j, k]
+            assert w1_hi[o] == np.float16(w[2][j, k])
+            assert abs(float(w1_hi[o]) + float(w1_lo[o]) - float(w[2][j, k])) <= abs(float(w[2][j, k])) * 2.0 ** -21 + 6e-8
     assert sorted(set(idx(j, k, 64) for j in range(64) for k in range(64))) == list(range(4096))   # a permutation
     assert np.array_equal(tail[:64], w[3]) and np.array_equal(tail[64:192], w[4].ravel())
     assert np.array_equal(tail[192:194], w[5]) and np.allclose(tail[194:196], np.exp(w[6]), rtol=1e-6)

@@ -14,9 +14,12 @@ import json
 import os
 import shutil
 import subprocess
+import sys
 from collections import defaultdict
 
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, REPO)
+from bench import kernel_source_hash  # noqa: E402  (bench.py reports roofline.traffic only while the sources are unchanged)
 
 METRICS = [
     "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "launch__registers_per_thread",
@@ -42,7 +45,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("rep")
     ap.add_argument("launches", nargs="?")
-    ap.add_argument("--tag", default="r01")
+    ap.add_argument("--tag", default="r02")
+    ap.add_argument("--name", default="step_kernel", help="file stem: profiles/<tag>_<name>.{json,md}")
     ap.add_argument("--envs", type=int, default=65536)
     ap.add_argument("--algo-bytes", type=float, default=796.0)
     args = ap.parse_args()
@@ -79,6 +83,7 @@ def main():
     dur = sum(l["gpu__time_duration.sum"] * unit_scale("gpu__time_duration.sum") for l in launches) / len(launches)
     summary = {
         "tag": args.tag, "source": os.path.basename(args.rep), "kernel": first["kernel"], "launches_profiled": len(launches),
+        "kernel_source_hash": kernel_source_hash(),
         "envs_per_launch": args.envs,
         "dram_bytes_per_launch": traffic, "dram_bytes_per_env_step": traffic / args.envs,
         "algorithmic_bytes_per_env_step": args.algo_bytes, "traffic_over_algorithmic": traffic / (args.envs * args.algo_bytes),
@@ -101,7 +106,7 @@ def main():
         tot = sum(v[1] for v in agg.values()) or 1.0
         summary["launch_list"] = [{"kernel": k, "launches": v[0], "total_ns": v[1], "share_pct": round(100 * v[1] / tot, 2)}
                                   for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])]
-    with open(os.path.join(out_dir, "%s_step_kernel.json" % args.tag), "w") as f:
+    with open(os.path.join(out_dir, "%s_%s.json" % (args.tag, args.name)), "w") as f:
         json.dump(summary, f, indent=1)
     L = summary["launch"]
     md = ["# %s — ncu summary of `%s`" % (args.tag, first["kernel"]), "",
@@ -121,7 +126,7 @@ def main():
         for e in summary["launch_list"][:8]:
             md.append("| `%s` | %d | %.2f %% |" % (e["kernel"][:70], e["launches"], e["share_pct"]))
         md.append("")
-    with open(os.path.join(out_dir, "%s_step_kernel.md" % args.tag), "w") as f:
+    with open(os.path.join(out_dir, "%s_%s.md" % (args.tag, args.name)), "w") as f:
         f.write("\n".join(md))
     print("\n".join(md))
 
