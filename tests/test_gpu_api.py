@@ -46,7 +46,7 @@ def test_vec_env_contract(pkg):
     assert seen_done > 50
     st = env.episode_stats()
     assert st["episodes"] == seen_done and st["n_successful_runs"] + st["n_failed_runs"] >= seen_done
-    assert env.seed(0)[:2] == [3, 4] and env.env_is_wrapped(object) == [False] * n
+    assert env.seed()[:2] == [3, 4] and env.env_is_wrapped(object) == [False] * n
     assert env.get_attr("num_envs", [0, 1]) == [n, n]
     env.step_async(np.zeros((n, 2), np.float32))
     env.step_wait()

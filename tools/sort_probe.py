@@ -73,3 +73,17 @@ run("identity", ident)
 run("nfev_desc", np.argsort(-nfev, kind="stable"))
 run("nobs_then_nfev", np.lexsort((-nfev, -nobs)))
 run("random", np.random.RandomState(0).permutation(E))
+
+
+def blockwise(keyfn, B=128):
+    out = []
+    for b in range(0, E, B):
+        idx = np.arange(b, min(b + B, E))
+        out.append(idx[keyfn(idx)])
+    return np.concatenate(out)
+
+
+run("block128_nfev_desc", blockwise(lambda idx: np.argsort(-nfev[idx], kind="stable")))
+run("block128_nobs_then_nfev", blockwise(lambda idx: np.lexsort((-nfev[idx], -nobs[idx]))))
+run("block128_nfev_then_nobs", blockwise(lambda idx: np.lexsort((-nobs[idx], -nfev[idx]))))
+run("global_nfev_then_nobs", np.lexsort((-nobs, -nfev)))
