@@ -140,16 +140,6 @@ __device__ __forceinline__ double u01_from_bits(uint32_t hi, uint32_t lo)
     return ((double)(hi >> 5) * 67108864.0 + (double)(lo >> 6)) * (1.0 / 9007199254740992.0);
 }
 
-// variates from uniforms: ONE definition each, used by the sequential stream and by the random-access (warp-
-// cooperative) sampler, so that both round identically
-__device__ __forceinline__ double uniform_from(double u, double lo, double hi) { return lo + (hi - lo) * u; }
-__device__ __forceinline__ double normal_from(double u1, double u2, double mu, double sd)
-{
-    // Box-Muller (cosine branch)
-    const double z = sqrt(-2.0 * log(1.0 - u1)) * cos(D2D_TWO_PI * u2);
-    return mu + sd * z;
-}
-
 // Sequential draws d = 0,1,2,... of one (env, episode): block d/2 of the stream.
 struct ResetRng {
     uint32_t env, episode, k0, k1, blk;
@@ -167,26 +157,13 @@ struct ResetRng {
         has = true;
         return u01_from_bits(o[0], o[1]);
     }
-    // index of the next draw, and repositioning (draw d lives in block d/2: first half if d is even)
-    __device__ uint32_t position() const { return 2u * blk - (has ? 1u : 0u); }
-    __device__ void seek(uint32_t d)
-    {
-        blk = d >> 1; has = false;
-        if (d & 1u) (void)u01();          // consumes the block's first half, leaves the second as the spare
-    }
-    // draw d without touching the sequential state
-    __device__ double u01_at(uint32_t d) const
-    {
-        uint32_t o[4];
-        philox4x32_10(env, episode, d >> 1, D2D_STREAM_RESET, k0, k1, o);
-        return (d & 1u) ? u01_from_bits(o[2], o[3]) : u01_from_bits(o[0], o[1]);
-    }
-    __device__ double uniform(double lo, double hi) { return uniform_from(u01(), lo, hi); }
-    // consumes two draws
+    __device__ double uniform(double lo, double hi) { return lo + (hi - lo) * u01(); }
+    // Box-Muller (cosine branch), consumes two draws
     __device__ double normal(double mu, double sd)
     {
-        const double u1 = u01(), u2 = u01();
-        return normal_from(u1, u2, mu, sd);
+        double u1 = u01(), u2 = u01();
+        double z = sqrt(-2.0 * log(1.0 - u1)) * cos(D2D_TWO_PI * u2);
+        return mu + sd * z;
     }
     __device__ int randint(int a, int b)   // inclusive, like random.randint
     {
@@ -999,21 +976,6 @@ __device__ __forceinline__ void path_point_and_gradient(const V &v, double u, do
 // generate_obstacles_around_path (obstacles.py:58-89): rejection sampler.  The offset direction
 // (cos, sin)(atan2(gy, gx) - pi/2) is (gy, -gx)/|g|, evaluated without the transcendental round trip
 // (differs from the reference's value by rounding only; reset parity tolerance 1e-7 px).
-// One attempt from its three variates (u ~ U(0.2L, 0.9L), offset ~ N(mean, sd), radius ~ U(10, 50)): the candidate
-// circle and whether obstacles.py:71-86 keeps it.  Shared by the serial and the warp-cooperative sampler, so that
-// both produce the same obstacles bit for bit.
-__device__ __forceinline__ bool obstacle_attempt(EnvView &ev, double u_obs, double dist, double size, bool on_path,
-                                                 double &ox, double &oy)
-{
-    double gx, gy, x, y;
-    path_point_and_gradient(ev, u_obs, x, y, gx, gy);
-    if (on_path) { ox = x; oy = y; return true; }
-    const double inv_g = rsqrt(gx * gx + gy * gy);
-    ox = x + dist * (gy * inv_g); oy = y + dist * (-gx * inv_g);
-    const double ddx = ox - x, ddy = oy - y;
-    return sqrt(ddx * ddx + ddy * ddy) > size + 10.0;
-}
-
 __device__ __forceinline__ int sample_obstacles(const D2dParams &p, EnvView &ev, ResetRng &rng, int slot, int count,
                                                 double mean, double sd, bool on_path)
 {
@@ -1024,57 +986,22 @@ __device__ __forceinline__ int sample_obstacles(const D2dParams &p, EnvView &ev,
         const double u_obs = rng.uniform(0.20 * L, 0.90 * L);
         const double dist = rng.normal(mean, sd);
         const double size = rng.uniform(10.0, 50.0);
-        double ox, oy;
-        if (obstacle_attempt(ev, u_obs, dist, size, on_path, ox, oy)) {
+        double gx, gy, x, y;
+        path_point_and_gradient(ev, u_obs, x, y, gx, gy);
+        if (on_path) {
+            p.obxy[ev.row16(slot)] = make_double2(x, y);
+            p.obr[ev.row8(slot)] = size;
+            slot++; made++;
+            continue;
+        }
+        const double inv_g = rsqrt(gx * gx + gy * gy);
+        const double ox = x + dist * (gy * inv_g), oy = y + dist * (-gx * inv_g);
+        const double ddx = ox - x, ddy = oy - y;
+        if (sqrt(ddx * ddx + ddy * ddy) > size + 10.0) {
             p.obxy[ev.row16(slot)] = make_double2(ox, oy);
             p.obr[ev.row8(slot)] = size;
             slot++; made++;
         }
-    }
-    return slot;
-}
-
-// The same sampler run by a whole warp for ONE environment (off-path obstacles): lane l evaluates attempt a0 + l,
-// whose four variates are draws draw0 + 4 (a0 + l) .. + 3 of the env's counter-based stream; the accepted attempts
-// are kept in attempt order until `count` circles exist, exactly like the serial loop (which stops drawing right
-// after the attempt that completes the count).  All arguments are warp-uniform.  Returns the new slot count and,
-// through `draws_used`, how far the serial stream has advanced.  The obstacle rejection loop has a data-dependent
-// trip count (~1.4 attempts per circle, up to 31 circles) and was the longest chain of the refill roles.
-__device__ __noinline__ int sample_obstacles_coop(const D2dParams &p, EnvView &ev, const ResetRng &rng, uint32_t draw0,
-                                                     int slot, int count, double mean, double sd, uint32_t &draws_used)
-{
-    const double L = ev.us(ev.n_wps() - 1);
-    const int lane = threadIdx.x & 31;
-    int made = 0;
-    uint32_t a0 = 0;
-    draws_used = 0;
-    while (made < count && slot < D2D_MAX_OBS_ENV && a0 < 4096u) {
-        const uint32_t d = draw0 + 4u * (a0 + (uint32_t)lane);
-        const double u_obs = uniform_from(rng.u01_at(d), 0.20 * L, 0.90 * L);
-        const double dist = normal_from(rng.u01_at(d + 1), rng.u01_at(d + 2), mean, sd);
-        const double size = uniform_from(rng.u01_at(d + 3), 10.0, 50.0);
-        double ox, oy;
-        const bool ok = obstacle_attempt(ev, u_obs, dist, size, false, ox, oy);
-        const unsigned acc = __ballot_sync(0xffffffffu, ok);
-        const int need = min(count - made, D2D_MAX_OBS_ENV - slot);
-        const int rank = __popc(acc & ((1u << lane) - 1u));
-        if (ok && rank < need) {
-            p.obxy[ev.row16(slot + rank)] = make_double2(ox, oy);
-            p.obr[ev.row8(slot + rank)] = size;
-        }
-        const int got = __popc(acc);
-        if (got >= need) {
-            // the attempt that completed the count: the need-th accepted lane of this batch
-            unsigned m = acc;
-            for (int k = 1; k < need; k++) m &= m - 1;
-            const int last = __ffs(m) - 1;
-            slot += need; made += need;
-            draws_used = 4u * (a0 + (uint32_t)last + 1u);
-            return slot;
-        }
-        slot += got; made += got;
-        a0 += 32u;
-        draws_used = 4u * a0;
     }
     return slot;
 }
@@ -1088,17 +1015,8 @@ struct ResetOut {
     int n_obs;
 };
 
-// Off-path obstacles the caller will draw itself, with the whole warp (sample_obstacles_coop), instead of the lane:
-// `count` circles starting at draw `draw0` of the episode's stream, then (stage_5) one on-path circle.
-struct ObstaclePlan {
-    int count;
-    uint32_t draw0;
-    int then_on_path;
-};
-
 template <bool PER_ENV>
-__device__ __noinline__ ResetOut reset_env(const D2dParams &p, int64_t i, int episode, int par, double *us_s,
-                                           ObstaclePlan *plan = nullptr)
+__device__ __noinline__ ResetOut reset_env(const D2dParams &p, int64_t i, int episode, int par, double *us_s)
 {
     const D2dConst &c = p.c;
     ResetRng rng((uint32_t)(c.env_id_base + i), (uint32_t)episode, c.seed_lo, c.seed_hi);
@@ -1162,10 +1080,7 @@ __device__ __noinline__ ResetOut reset_env(const D2dParams &p, int64_t i, int ep
         sx = rng.uniform(100.0, c.W - 100.0);
         sy = rng.uniform(100.0, c.H - 100.0);
     } else if (c.stage == 3) {                                    // env:334-347
-        if (rng.u01() < c.spawn_chance) {
-            if (plan) { plan->count = 1; plan->draw0 = rng.position(); plan->then_on_path = 0; }
-            else n_obs = sample_obstacles(p, ev, rng, 0, 1, 0.0, 100.0, false);
-        }
+        if (rng.u01() < c.spawn_chance) n_obs = sample_obstacles(p, ev, rng, 0, 1, 0.0, 100.0, false);
     } else if (c.stage == 4) {                                    // env:348-361
         if (rng.u01() < c.spawn_chance) n_obs = sample_obstacles(p, ev, rng, 0, 1, 0.0, 0.0, true);
     } else if (c.stage == 5) {                                    // env:362-372
@@ -1176,12 +1091,8 @@ __device__ __noinline__ ResetOut reset_env(const D2dParams &p, int64_t i, int ep
             int want = (int)ceil(nn);                             // `while num_obstacles < n` with float n
             if (want < 0) want = 0;                               // nn == -3 exactly
             if (want > D2D_MAX_OBS_ENV - 1) want = D2D_MAX_OBS_ENV - 1;
-            if (plan && want > 0) {
-                plan->count = want; plan->draw0 = rng.position(); plan->then_on_path = 1;
-            } else {
-                n_obs = sample_obstacles(p, ev, rng, 0, want, 0.0, 100.0, false);
-                n_obs = sample_obstacles(p, ev, rng, n_obs, 1, 0.0, 0.0, true);
-            }
+            n_obs = sample_obstacles(p, ev, rng, 0, want, 0.0, 100.0, false);
+            n_obs = sample_obstacles(p, ev, rng, n_obs, 1, 0.0, 0.0, true);
         }
     }
     return ResetOut{sx, sy, sa, n_obs};
