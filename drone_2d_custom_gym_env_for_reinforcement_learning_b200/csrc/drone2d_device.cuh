@@ -99,19 +99,20 @@ __device__ __noinline__ double2 sincos2(double a)
 
 __device__ __noinline__ double atan2_ool(double y, double x) { return atan2(y, x); }
 
-// (sin, cos) of ssa((atan2(dy, dx) - alpha) - off): the bearing pattern of env:695-698, 724-727, 752-763
-__device__ __noinline__ double2 bearing_sincos(double dy, double dx, double alpha, double off)
+// (sin, cos) of ssa((atan2(dy, dx) - alpha) - off) is the bearing pattern of env:695-698, 724-727, 752-763.
+// Evaluated without transcendentals: (sin, cos) of atan2(dy, dx) - beta is the unit vector (dx, dy)/r rotated by
+// -beta, with (cos beta, sin beta) = sign * (cb, sb) already known (the frame's rotation; sign = -1 folds the "- pi" of
+// env:695).  Differs from the atan2 -> ssa -> sincos route of the reference by rounding only (the wrap of ssa does not
+// change sin / cos); ~35 instructions instead of ~330.  atan2(0, 0) = 0, i.e. the unit vector (1, 0), for a null vector.
+__device__ __forceinline__ double2 bearing_rot(double dy, double dx, double cb, double sb, double sign)
 {
-    const double ang = ssa((atan2(dy, dx) - alpha) - off);
-    double sn, cs;
-    sincos(ang, &sn, &cs);
-    return make_double2(sn, cs);
-}
-
-// (atan2(s, c) + 2 pi) % (2 pi): the angle decode of env:435, 444-445, 482
-__device__ __noinline__ double atan2_mod2pi(double sn, double cs)
-{
-    return py_mod_pos(atan2(sn, cs) + D2D_TWO_PI, D2D_TWO_PI);
+    const double r2 = dx * dx + dy * dy;
+    double ux = 1.0, uy = 0.0;
+    if (r2 > 0.0) {
+        const double inv = 1.0 / sqrt(r2);
+        ux = dx * inv; uy = dy * inv;
+    }
+    return make_double2(sign * (uy * cb - ux * sb), sign * (ux * cb + uy * sb));
 }
 
 // ---------------------------------------------------------------------------
@@ -804,7 +805,7 @@ __device__ __forceinline__ void observe(const V &v, const D2dConst &c, EnvState 
     for (int j = 0; j < 3; j++) {
         double dn = 1.0, sa = 0.0, ca = 0.0;
         if (nr.idx[j] >= 0) {
-            const double2 sc = bearing_sincos(y - nr.oy[j], x - nr.ox[j], alpha, D2D_PI);
+            const double2 sc = bearing_rot(y - nr.oy[j], x - nr.ox[j], rc0, rs0, -1.0);      // env:693-698, "- alpha - pi"
             dn = m1to1(nr.d[j], 0.0, c.diag, c.r_diag);
             sa = sc.x; ca = sc.y;
         }
@@ -815,7 +816,7 @@ __device__ __forceinline__ void observe(const V &v, const D2dConst &c, EnvState 
 
     // env:723-727
     {
-        const double2 sc = bearing_sincos(s.vy[0], s.vx[0], alpha, 0.0);
+        const double2 sc = bearing_rot(s.vy[0], s.vx[0], rc0, rs0, 1.0);
         ax.o17 = sc.x; ax.o18 = sc.y;
         put(17, ax.o17); put(18, ax.o18);
     }
@@ -839,16 +840,15 @@ __device__ __forceinline__ void observe(const V &v, const D2dConst &c, EnvState 
     if (s.flags & D2D_F_LATCHED) { lx = tgt.x; ly = tgt.y; }
     put(21, m1to1(lx, 0.0, W, c.r_W)); put(22, m1to1(ly, 0.0, H, c.r_H));
 
-    // env:752-763: R_w_b rotates by +alpha (transformations.py:9-11)
+    // env:752-763: R_w_b rotates the vector by +alpha (transformations.py:9-11) and the frame angle is subtracted
+    // again: what is left is the WORLD bearing of the vector itself, i.e. its unit vector (rotation by 0)
     {
-        const double dx = lx - x, dy = ly - y;
-        const double2 sc = bearing_sincos(rs0 * dx + rc0 * dy, rc0 * dx - rs0 * dy, alpha, 0.0);
+        const double2 sc = bearing_rot(ly - y, lx - x, 1.0, 0.0, 1.0);
         ax.o23 = sc.x; ax.o24 = sc.y;
         put(23, ax.o23); put(24, ax.o24);
     }
     {
-        const double dx = cx - x, dy = cy - y;
-        const double2 sc = bearing_sincos(rs0 * dx + rc0 * dy, rc0 * dx - rs0 * dy, alpha, 0.0);
+        const double2 sc = bearing_rot(cy - y, cx - x, 1.0, 0.0, 1.0);
         put(25, sc.x); put(26, sc.y);
     }
 }
@@ -871,16 +871,16 @@ __device__ __forceinline__ void reward_and_done(const D2dConst &c, EnvState &s, 
     const double alpha = o.o3 * D2D_PI;
     const double tdx = invm1to1(o.o4, 0.0, W), tdy = invm1to1(o.o5, 0.0, H);
     const double pos_x = invm1to1(o.o6, 0.0, W), pos_y = invm1to1(o.o7, 0.0, H);
-    const double vel_angle = atan2_mod2pi(o.o17 * D2D_PI, o.o18 * D2D_PI);
     const double cpx = invm1to1(o.o19, 0.0, W), cpy = invm1to1(o.o20, 0.0, H);
-    const double la_angle = atan2_mod2pi(o.o23, o.o24);
+    // env:435,444-445,482 decode velocity / look-ahead / obstacle angles with arctan2 only to take differences of
+    // them (env:484, 537): |((a - b + pi) % 2 pi) - pi| = atan2(|sin(a - b)|, cos(a - b)), and sin / cos of the
+    // difference follow from the (sin, cos) pairs of the observation -- same value up to rounding, one atan2 instead of
+    // three (and none for the progression reward, which only needs the cosine)
 
     double lambda_PA = 1.0, lambda_CA = 1.0, r_CA = 0.0, d1 = CUDART_INF;
     if (has_obstacles) {                                          // env:462-523
         d1 = invm1to1(o.o8, 0.0, c.diag);
-        const double obs_angle = atan2_mod2pi(o.o9, o.o10);
-        const double angle_diff =
-            fabs((py_mod_pos(obs_angle - vel_angle + D2D_PI, D2D_TWO_PI) - D2D_PI) * (180.0 / D2D_PI));
+        const double sin_d = o.o9 * o.o18 - o.o10 * o.o17, cos_d = o.o10 * o.o18 + o.o9 * o.o17;   // obstacle - velocity
         const double DR = c.danger_range, DA = c.danger_angle, kk = c.k_ca;
         if (d1 < DR && c.use_Lambda) {
             lambda_PA = div_const(d1, DR, c.r_DR) / 2.0;
@@ -888,6 +888,7 @@ __device__ __forceinline__ void reward_and_done(const D2dConst &c, EnvState &s, 
             lambda_CA = 1.0 - lambda_PA;
         }
         if (d1 < DR) {
+            const double angle_diff = atan2_ool(fabs(sin_d), cos_d) * (180.0 / D2D_PI);
             double range_rew = -(((DR + kk * DR) / (d1 + kk * DR)) - 1.0);
             double angle_rew = -(((DA + kk * DA) / (angle_diff + kk * DA)) - 1.0);
             if (angle_rew > 0.0) angle_rew = 0.0;
@@ -901,8 +902,8 @@ __device__ __forceinline__ void reward_and_done(const D2dConst &c, EnvState &s, 
     const double r_PA = -(2.0 * div_const(clipd(dist_from_path, 0.0, c.PA_band_edge), c.PA_band_edge, c.r_PA) - 1.0) * c.PA_scale;
     // env:534-539
     const double velocity = sqrt(vel_x * vel_x + vel_y * vel_y);
-    const double vel_LA_diff = fabs(py_mod_pos(la_angle - vel_angle + D2D_PI, D2D_TWO_PI) - D2D_PI);
-    const double r_PP = clipd(cos(vel_LA_diff) * (velocity * c.PP_vel_scale), c.PP_rew_min, c.PP_rew_max);
+    const double cos_vel_LA = o.o24 * o.o18 + o.o23 * o.o17;             // cos(look-ahead angle - velocity angle)
+    const double r_PP = clipd(cos_vel_LA * (velocity * c.PP_vel_scale), c.PP_rew_min, c.PP_rew_max);
     // env:543-570
     int bits = 0;
     double r_coll = 0.0, r_end = 0.0, r_AA = 0.0;

@@ -218,3 +218,30 @@ def test_seed_rekeys_the_reset_stream():
     obs, rew, dones, infos = env.step(np.zeros((64, 2), np.float32))       # the rebuilt handle steps and fills infos
     assert obs.shape == (64, 27) and np.isfinite(obs).all()
     env.close()
+
+
+def test_flight_path_ring_shorter_than_the_episode_keeps_the_last_positions():
+    """A ring of K < T positions: the info carries the last K positions of the episode, oldest first."""
+    pkg = importlib.import_module(PKG)
+    n, T, K = 32, 40, 16
+    env = pkg.Drone2dVecEnv(n, seed=9, mode="test", scenario="corridor", n_steps=T, info_mode="episode")
+    env.enable_flight_paths(ring=K)
+    env.reset()
+    track = [[] for _ in range(n)]
+    checked = 0
+    for t in range(T + 1):
+        obs, rew, dones, infos = env.step(np.zeros((n, 2), np.float32))
+        st = env.get_state()
+        for i in range(n):
+            if dones[i]:
+                fp = np.array(infos[i]["flight_path"])
+                steps = infos[i]["env_steps"]
+                want = np.array(track[i], dtype=np.float64).reshape(-1, 2)[-(min(K, steps) - 1):] if min(K, steps) > 1 else np.zeros((0, 2))
+                assert len(fp) == min(K, steps)
+                assert np.abs(fp[:-1] - want).max() < 1e-3          # all but the terminal position (state was reset)
+                track[i] = []
+                checked += 1
+            else:
+                track[i].append((st[i, 0], 1300.0 - st[i, 1]))
+    assert checked >= n
+    env.close()
