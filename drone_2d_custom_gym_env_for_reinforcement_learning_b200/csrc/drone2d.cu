@@ -272,7 +272,7 @@ __global__ void __launch_bounds__(D2D_BLOCK, D2D_MIN_BLOCKS) d2d_step_kernel(con
         const long long t_obs = clock64();
 
         StepResult r;
-        reward_and_done(c, s, ax, v.n_obs() > 0, r);
+        reward_and_done(c, s, ax, v.n_obs() > 0, rs0, r);
         p.reward[i] = (float)r.reward;
         p.done[i] = r.done ? 1 : 0;
         if (p.info && (r.done || !p.info_done_only)) {

@@ -863,7 +863,7 @@ struct StepResult {
 };
 
 __device__ __forceinline__ void reward_and_done(const D2dConst &c, EnvState &s, const ObsAux &o, bool has_obstacles,
-                                                StepResult &r)
+                                                double sin_alpha, StepResult &r)
 {
     const double W = c.W, H = c.H;
     // env:423-445: decode the observation back to physical units
@@ -909,8 +909,10 @@ __device__ __forceinline__ void reward_and_done(const D2dConst &c, EnvState &s, 
     double r_coll = 0.0, r_end = 0.0, r_AA = 0.0;
     if (s.flags & D2D_F_COLLIDED) { r_coll = c.rew_collision; bits |= 1; }
     if (fabs(tdx) < c.reach_end_radius && fabs(tdy) < c.reach_end_radius) { r_end = c.rew_reach_end; bits |= 2; }
-    if (alpha > c.AA_band) r_AA = -sin(alpha);
-    if (alpha < -c.AA_band) r_AA = sin(alpha);
+    // env:557-565: np.sin(alpha) of the decoded angle; the sine of the frame angle is already known from the rigid-body
+    // step (the decode alpha/pi*pi moves the angle by an ulp at most: rounding-level difference)
+    if (alpha > c.AA_band) r_AA = -sin_alpha;
+    if (alpha < -c.AA_band) r_AA = sin_alpha;
     if (fabs(alpha) >= c.AA_angle) { r_AA = c.rew_AA; bits |= 8; }
     if (s.steps == c.n_steps) bits |= 4;
     // env:572
