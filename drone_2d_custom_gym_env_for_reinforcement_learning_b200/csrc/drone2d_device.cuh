@@ -99,6 +99,33 @@ __device__ __noinline__ double2 sincos2(double a)
 
 __device__ __noinline__ double atan2_ool(double y, double x) { return atan2(y, x); }
 
+// sin / cos of a body angle, inline (the rigid-body step needs four per step, at a point where ~60 registers are live:
+// every out-of-line call there saves and restores them).  One Cody-Waite reduction by pi/2 and the fdlibm kernels on
+// |r| <= pi/4 (error < 1 ulp: rounding-level difference from the reference's libm calls); body angles stay within a
+// few radians (|alpha| >= pi/2 ends the episode), anything larger takes the library route.
+__device__ __forceinline__ void sincos_body(double a, double &sn, double &cs)
+{
+    if (fabs(a) > 6.0) { const double2 sc = sincos2(a); sn = sc.x; cs = sc.y; return; }
+    const double q = rint(a * 0.63661977236758134308);                        // 2 / pi
+    double r = fma(-q, 1.57079632679489655800e+00, a);
+    r = fma(-q, 6.12323399573676603587e-17, r);
+    const double z = r * r;
+    double ps = 1.58969099521155010221e-10;
+    ps = fma(ps, z, -2.50507602534068634195e-08); ps = fma(ps, z, 2.75573137070700676789e-06);
+    ps = fma(ps, z, -1.98412698298579493134e-04); ps = fma(ps, z, 8.33333333332248946124e-03);
+    ps = fma(ps, z, -1.66666666666666324348e-01);
+    const double sr = fma(r * z, ps, r);
+    double pc = -1.13596475577881948265e-11;
+    pc = fma(pc, z, 2.08757232129817482790e-09); pc = fma(pc, z, -2.75573143513906633035e-07);
+    pc = fma(pc, z, 2.48015872894767294178e-05); pc = fma(pc, z, -1.38888888888741095749e-03);
+    pc = fma(pc, z, 4.16666666666666019037e-02);
+    const double cr = fma(z * z, pc, fma(-0.5, z, 1.0));
+    const int k = (int)q & 3;
+    const double s0 = (k & 1) ? cr : sr, c0 = (k & 1) ? sr : cr;
+    sn = (k & 2) ? -s0 : s0;
+    cs = ((k + 1) & 2) ? -c0 : c0;
+}
+
 // (sin, cos) of ssa((atan2(dy, dx) - alpha) - off) is the bearing pattern of env:695-698, 724-727, 752-763.
 // Evaluated without transcendentals: (sin, cos) of atan2(dy, dx) - beta is the unit vector (dx, dy)/r rotated by
 // -beta, with (cos beta, sin beta) = sign * (cb, sb) already known (the frame's rotation; sign = -1 folds the "- pi" of
@@ -588,8 +615,8 @@ __device__ __forceinline__ void physics_step(EnvState &s, const D2dConst &c, dou
     // cpBodyApplyForceAtLocalPoint on the frame, transform of the CURRENT pose
     double fx, fy, tq;
     {
-        const double2 sc = sincos2(s.an[0]);
-        const double ry = sc.x, rx = sc.y;
+        double ry, rx;
+        sincos_body(s.an[0], ry, rx);
         const double fwxL = -ry * FL, fwyL = rx * FL, fwxR = -ry * FR, fwyR = rx * FR;
         const double rLx = (rx * -c.R + s.px[0]) - s.px[0], rLy = (ry * -c.R + s.py[0]) - s.py[0];
         const double rRx = (rx * c.R + s.px[0]) - s.px[0], rRy = (ry * c.R + s.py[0]) - s.py[0];
@@ -604,8 +631,7 @@ __device__ __forceinline__ void physics_step(EnvState &s, const D2dConst &c, dou
         s.px[b] = s.px[b] + s.vx[b] * dt;
         s.py[b] = s.py[b] + s.vy[b] * dt;
         s.an[b] = s.an[b] + s.om[b] * dt;
-        const double2 sc = sincos2(s.an[b]);
-        rs[b] = sc.x; rc[b] = sc.y;
+        sincos_body(s.an[b], rs[b], rc[b]);
     }
     rc0 = rc[0]; rs0 = rs[0];
 
