@@ -84,6 +84,13 @@ __device__ __forceinline__ double m1to1(double v, double lo, double d, double rd
 __device__ __forceinline__ double invm1to1(double v, double lo, double hi) { return (v + 1.0) * (hi - lo) / 2.0 + lo; }
 __device__ __forceinline__ double clipd(double v, double lo, double hi) { return v < lo ? lo : (v > hi ? hi : v); }
 // min / max of finite values (fmin/fmax carry NaN handling that costs ~8 instructions per call)
+// |x|, -x and x with a given sign as integer operations on the high word: ptxas materialises
+// fabs()/negation of a double as DADD (an FP64-pipe instruction with FP64 latency) whenever the
+// result feeds a select; these are single ALU operations.  Bit-identical for every input.
+__device__ __forceinline__ double abs_b(double x) { return __hiloint2double(__double2hiint(x) & 0x7fffffff, __double2loint(x)); }
+__device__ __forceinline__ double neg_b(double x) { return __hiloint2double(__double2hiint(x) ^ 0x80000000, __double2loint(x)); }
+__device__ __forceinline__ double neg_if(double x, bool c) { return __hiloint2double(__double2hiint(x) ^ (c ? 0x80000000 : 0), __double2loint(x)); }
+
 __device__ __forceinline__ double min_f(double a, double b) { return (b < a) ? b : a; }
 __device__ __forceinline__ double max_f(double a, double b) { return (b > a) ? b : a; }
 
@@ -441,8 +448,9 @@ struct PathCursor {
 // (_minimize_scalar_bounded, scipy/optimize/_optimize.py:2289-2440) on
 // [-10, L+10], xatol = 1e-6, maxfun = 500.  Same floating-point operations in the same
 // order as the reference; the control flow is arranged around ONE evaluation site (the
-// initial point is the first trip of the loop) and the path point of the best iterate is
-// kept, so get_closest_position (predef_path.py:251-255) needs no further evaluation.
+// initial point is the first trip of the loop); get_closest_position (predef_path.py:251-255)
+// is one more evaluation at the minimiser after the loop (4 selects per trip cheaper than
+// carrying the best point through the loop).
 // Every lane runs its own iteration count (typically 10-47).
 template <class V>
 __device__ __forceinline__ double closest_u(PathCursor<V> &pc, double px, double py, int &nfev, double &bx, double &by)
@@ -456,44 +464,20 @@ __device__ __forceinline__ double closest_u(PathCursor<V> &pc, double px, double
     double nfc = fulc, xf = fulc;
     double rat = 0.0, e = 0.0;
     double x = xf;
-    double fx = 0.0, ffulc = 0.0, fnfc = 0.0;
-    int num = 0;
-    bx = 0.0; by = 0.0;
-#pragma unroll 1
-    for (;;) {
-        // objective: np.linalg.norm(path(x) - pos) = sqrt(fma(dy, dy, dx*dx))  (BLAS ddot, predef_path.py:246)
+    double fx, ffulc, fnfc;
+    {
         double ex, ey;
         pc.eval(x, ex, ey);
         const double dx = S::sub(ex, px), dy = S::sub(ey, py);
-        const double fu = S::sqrt(S::fma(dy, dy, S::mul(dx, dx)));
-        if (num == 0) {
-            fx = fu; ffulc = fu; fnfc = fu; bx = ex; by = ey;
-        } else {
-            // scipy's update rules (`if fu <= fx: ... else: ...`, _optimize.py:2393-2412) as one
-            // branch-free dataflow: the lanes of a warp take different branches on almost every
-            // trip, and the branchy form costs ~90 register moves per trip on top of both paths.
-            const bool better = (fu <= fx);
-            const bool right = (x >= xf);
-            const bool c1 = (fu <= fnfc) || (nfc == xf);                          // worse: new point becomes nfc
-            const bool c2 = (fu <= ffulc) || (fulc == xf) || (fulc == nfc);       // worse: new point becomes fulc
-            const bool shift = better || c1;                                      // (nfc, fnfc) -> (fulc, ffulc)
-            const double t = better ? xf : x;                                     // the new bracket end
-            const double na = (better == right) ? t : a;
-            const double nb = (better != right) ? t : b;
-            const double n_fulc = shift ? nfc : (c2 ? x : fulc);
-            const double n_ffulc = shift ? fnfc : (c2 ? fu : ffulc);
-            const double n_nfc = better ? xf : (c1 ? x : nfc);
-            const double n_fnfc = better ? fx : (c1 ? fu : fnfc);
-            a = na; b = nb;
-            fulc = n_fulc; ffulc = n_ffulc; nfc = n_nfc; fnfc = n_fnfc;
-            xf = better ? x : xf; fx = better ? fu : fx;
-            bx = better ? ex : bx; by = better ? ey : by;
-        }
-        num += 1;
+        fx = ffulc = fnfc = S::sqrt(S::fma(dy, dy, S::mul(dx, dx)));
+    }
+    int num = 1;
+#pragma unroll 1
+    for (;;) {
         const double xm = S::mul(0.5, S::add(a, b));
         const double tol1 = S::add(S::mul(sqrt_eps, fabs(xf)), xatol_3);
         const double tol2 = S::mul(2.0, tol1);
-        if (num > 1 && num >= maxfun) break;
+        if (num >= maxfun) break;
         if (!(fabs(S::sub(xf, xm)) > S::sub(tol2, S::mul(0.5, S::sub(b, a))))) break;
 
         bool golden = true;
@@ -502,8 +486,8 @@ __device__ __forceinline__ double closest_u(PathCursor<V> &pc, double px, double
             double q = S::mul(S::sub(xf, fulc), S::sub(fx, fnfc));
             double p = S::sub(S::mul(S::sub(xf, fulc), q), S::mul(S::sub(xf, nfc), r));
             q = S::mul(2.0, S::sub(q, r));
-            if (q > 0.0) p = -p;
-            q = fabs(q);
+            p = neg_if(p, q > 0.0);
+            q = abs_b(q);
             r = e;
             e = rat;
             if ((fabs(p) < fabs(S::mul(S::mul(0.5, q), r))) && (p > S::mul(q, S::sub(a, xf))) &&
@@ -513,7 +497,7 @@ __device__ __forceinline__ double closest_u(PathCursor<V> &pc, double px, double
                 x = S::add(xf, rat);
                 if ((S::sub(x, a) < tol2) || (S::sub(b, x) < tol2)) {
                     // si = sign(xm - xf) + ((xm - xf) == 0)
-                    rat = (S::sub(xm, xf) < 0.0) ? -tol1 : tol1;
+                    rat = neg_if(tol1, S::sub(xm, xf) < 0.0);
                 }
             }
         }
@@ -522,10 +506,36 @@ __device__ __forceinline__ double closest_u(PathCursor<V> &pc, double px, double
             rat = S::mul(golden_mean, e);
         }
         // x = xf + (sign(rat) + (rat == 0)) * max(|rat|, tol1)
-        const double mag = max_f(fabs(rat), tol1);
-        x = S::add(xf, (rat < 0.0) ? -mag : mag);
+        const double mag = max_f(abs_b(rat), tol1);
+        x = S::add(xf, neg_if(mag, rat < 0.0));
+
+        // objective: np.linalg.norm(path(x) - pos) = sqrt(fma(dy, dy, dx*dx))  (BLAS ddot, predef_path.py:246)
+        double ex, ey;
+        pc.eval(x, ex, ey);
+        const double dx = S::sub(ex, px), dy = S::sub(ey, py);
+        const double fu = S::sqrt(S::fma(dy, dy, S::mul(dx, dx)));
+        num += 1;
+        // scipy's update rules (`if fu <= fx: ... else: ...`, _optimize.py:2393-2412) as one
+        // branch-free dataflow: the lanes of a warp take different branches on almost every
+        // trip, and the branchy form costs ~90 register moves per trip on top of both paths.
+        const bool better = (fu <= fx);
+        const bool right = (x >= xf);
+        const bool c1 = (fu <= fnfc) || (nfc == xf);                          // worse: new point becomes nfc
+        const bool c2 = (fu <= ffulc) || (fulc == xf) || (fulc == nfc);       // worse: new point becomes fulc
+        const bool shift = better || c1;                                      // (nfc, fnfc) -> (fulc, ffulc)
+        const double t = better ? xf : x;                                     // the new bracket end
+        const double na = (better == right) ? t : a;
+        const double nb = (better != right) ? t : b;
+        const double n_fulc = shift ? nfc : (c2 ? x : fulc);
+        const double n_ffulc = shift ? fnfc : (c2 ? fu : ffulc);
+        const double n_nfc = better ? xf : (c1 ? x : nfc);
+        const double n_fnfc = better ? fx : (c1 ? fu : fnfc);
+        a = na; b = nb;
+        fulc = n_fulc; ffulc = n_ffulc; nfc = n_nfc; fnfc = n_fnfc;
+        xf = better ? x : xf; fx = better ? fu : fx;
     }
     nfev = num;
+    pc.eval(xf, bx, by);   // the path point of the minimiser: the same operations on the same u as inside the loop
     return xf;
 }
 
