@@ -121,6 +121,66 @@ __device__ __forceinline__ void stage_observe(const D2dParams &p, const D2dShare
     st_release_int4(&p.stg_meta[e], make_int4(target, sm.y, latch, target));
 }
 
+// ---- sample role of the step kernel: queue A of the previous step -> queue B of this step ----
+// Out of line: its registers (and spills) stay out of the main lanes' allocation.
+template <bool PER_ENV>
+__device__ __noinline__ void refill_sample_role(const D2dParams &p, double *s_us, int first, int total, int q_read, int q_write)
+{
+    const int tid = threadIdx.x;
+    const D2dConst &c = p.c;
+    int *qa = p.queue, *qb = p.queue + 3 * p.np, *qb_tgt = p.queue + 6 * p.np;
+    int *qa_cnt = p.qcount, *qb_cnt = p.qcount + 3;
+    // Each lane draws its task's path and spawn pose; the off-path obstacles of each task (a rejection loop
+    // with up to 31 circles, the longest chain of the refill roles) are then drawn by the WHOLE warp, one
+    // attempt per lane, with the same result as the lane's own loop (sample_obstacles_coop).
+    const int cnt = qa_cnt[q_read];
+    const int lane = tid & 31;
+    for (int it = 0;; it++) {
+        const int t = first + it * total;
+        const bool active = t < cnt;
+        if (!__any_sync(0xffffffffu, active)) break;
+        int e = 0, target = 0;
+        ResetOut ro = {0.0, 0.0, 0.0, 0};
+        ObstaclePlan plan = {0, 0u, 0};
+        if (active) {
+            e = qa[(int64_t)q_read * p.np + t];
+            target = p.meta[e].z + 1;
+            ro = reset_env<PER_ENV>(p, e, target, 1, &s_us[PER_ENV ? tid : 0], PER_ENV ? &plan : nullptr);
+        }
+        if (PER_ENV) {
+            __syncwarp();                                   // the tasks' tables and us[] columns are visible to the warp
+            unsigned todo = __ballot_sync(0xffffffffu, active && plan.count > 0);
+            while (todo) {
+                const int src = __ffs(todo) - 1;
+                todo &= todo - 1;
+                const int e_s = __shfl_sync(0xffffffffu, e, src), tgt_s = __shfl_sync(0xffffffffu, target, src);
+                const int cnt_s = __shfl_sync(0xffffffffu, plan.count, src);
+                const uint32_t draw0_s = __shfl_sync(0xffffffffu, plan.draw0, src);
+                EnvView ev{&p, (int64_t)e_s, 0, 1, &s_us[(tid & ~31) + src]};
+                const ResetRng rng((uint32_t)(c.env_id_base + e_s), (uint32_t)tgt_s, c.seed_lo, c.seed_hi);
+                uint32_t used;
+                const int n_made = sample_obstacles_coop(p, ev, rng, draw0_s, 0, cnt_s, 0.0, 100.0, used);
+                if (lane == src) { ro.n_obs = n_made; plan.draw0 += used; }
+            }
+            __syncwarp();
+            if (active && plan.count > 0 && plan.then_on_path) {
+                EnvView ev{&p, (int64_t)e, 0, 1, &s_us[tid]};
+                ResetRng rng((uint32_t)(c.env_id_base + e), (uint32_t)target, c.seed_lo, c.seed_hi);
+                rng.seek(plan.draw0);
+                ro.n_obs = sample_obstacles(p, ev, rng, ro.n_obs, 1, 0.0, 0.0, true);
+            }
+        }
+        if (active) {
+            p.stg_xy[e] = make_double2(ro.x, ro.y);
+            p.stg_an[e] = make_double2(ro.angle, 0.0);
+            p.stg_meta[e] = make_int4(-1, ro.n_obs, 1, target);
+            const int slot = atomicAdd(&qb_cnt[q_write], 1);
+            qb[(int64_t)q_write * p.np + slot] = e;
+            qb_tgt[(int64_t)q_write * p.np + slot] = target;
+        }
+    }
+}
+
 // The fused step: thrust -> cpSpaceStep -> sensor overlap -> nearest-3 ->
 // closest/look-ahead point -> 27-float observation -> reward -> termination ->
 // episode statistics -> auto-reset.  Grid = [sample blocks | observe blocks | main blocks]:
@@ -165,15 +225,7 @@ __global__ void __launch_bounds__(D2D_BLOCK, D2D_MIN_BLOCKS) d2d_step_kernel(con
         const int g = (sample_role ? blockIdx.x : blockIdx.x - p.refill_blocks) * D2D_BLOCK + tid;
         const int first = (g & 31) * n_warps + (g >> 5);        // task dealt to (warp, lane): lane-major over warps
         if (sample_role) {
-            // ---- sample role: queue A of the previous step -> queue B of this step ----
-            const int cnt = qa_cnt[q_read];
-            for (int t = first; t < cnt; t += total) {
-                const int e = qa[(int64_t)q_read * p.np + t];
-                stage_sample<PER_ENV>(p, e, &s_us[PER_ENV ? tid : 0]);
-                const int slot = atomicAdd(&qb_cnt[q_write], 1);
-                qb[(int64_t)q_write * p.np + slot] = e;
-                qb_tgt[(int64_t)q_write * p.np + slot] = p.stg_meta[e].w;
-            }
+            refill_sample_role<PER_ENV>(p, s_us, first, total, q_read, q_write);
         } else {
             // ---- observe role: queue B of the previous step ----
             const int cnt = qb_cnt[q_read];
@@ -206,7 +258,11 @@ __global__ void __launch_bounds__(D2D_BLOCK, D2D_MIN_BLOCKS) d2d_step_kernel(con
             const uint32_t base = (uint32_t)i;                  // live tables = buffer 0
             for (int k = 0; k < c.n_wps; k++) {
                 const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&s_us[k * D2D_BLOCK + tid]);
+#if D2D_L2_HINTS
+                asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 8, %2;" ::"r"(dst), "l"(p.us + base + (uint32_t)k * (uint32_t)p.np), "l"(l2_keep()));
+#else
                 asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(p.us + base + (uint32_t)k * (uint32_t)p.np));
+#endif
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
         }

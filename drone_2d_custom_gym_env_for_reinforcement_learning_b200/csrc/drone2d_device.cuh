@@ -175,6 +175,16 @@ __device__ __forceinline__ double u01_from_bits(uint32_t hi, uint32_t lo)
     return ((double)(hi >> 5) * 67108864.0 + (double)(lo >> 6)) * (1.0 / 9007199254740992.0);
 }
 
+// variates from uniforms: ONE definition each, used by the sequential stream and by the random-access (warp-
+// cooperative) sampler, so that both round identically
+__device__ __forceinline__ double uniform_from(double u, double lo, double hi) { return lo + (hi - lo) * u; }
+__device__ __forceinline__ double normal_from(double u1, double u2, double mu, double sd)
+{
+    // Box-Muller (cosine branch)
+    const double z = sqrt(-2.0 * log(1.0 - u1)) * cos(D2D_TWO_PI * u2);
+    return mu + sd * z;
+}
+
 // Sequential draws d = 0,1,2,... of one (env, episode): block d/2 of the stream.
 struct ResetRng {
     uint32_t env, episode, k0, k1, blk;
@@ -192,13 +202,26 @@ struct ResetRng {
         has = true;
         return u01_from_bits(o[0], o[1]);
     }
-    __device__ double uniform(double lo, double hi) { return lo + (hi - lo) * u01(); }
-    // Box-Muller (cosine branch), consumes two draws
+    // index of the next draw, and repositioning (draw d lives in block d/2: first half if d is even)
+    __device__ uint32_t position() const { return 2u * blk - (has ? 1u : 0u); }
+    __device__ void seek(uint32_t d)
+    {
+        blk = d >> 1; has = false;
+        if (d & 1u) (void)u01();          // consumes the block's first half, leaves the second as the spare
+    }
+    // draw d without touching the sequential state
+    __device__ double u01_at(uint32_t d) const
+    {
+        uint32_t o[4];
+        philox4x32_10(env, episode, d >> 1, D2D_STREAM_RESET, k0, k1, o);
+        return (d & 1u) ? u01_from_bits(o[2], o[3]) : u01_from_bits(o[0], o[1]);
+    }
+    __device__ double uniform(double lo, double hi) { return uniform_from(u01(), lo, hi); }
+    // consumes two draws
     __device__ double normal(double mu, double sd)
     {
-        double u1 = u01(), u2 = u01();
-        double z = sqrt(-2.0 * log(1.0 - u1)) * cos(D2D_TWO_PI * u2);
-        return mu + sd * z;
+        const double u1 = u01(), u2 = u01();
+        return normal_from(u1, u2, mu, sd);
     }
     __device__ int randint(int a, int b)   // inclusive, like random.randint
     {
@@ -225,6 +248,57 @@ struct SharedView {
     }
 };
 
+// L2 eviction hints.  The per-step working set (~85 MB at 65 536 envs) cycles through the L2 and is
+// re-read from DRAM every step.  Level 1: path rows / us[] -- the loads a search waits on
+// (PathCursor::locate) -- are evict_last, obstacle rows (read once per step, front to back) evict_first.
+// Level 2 (default): the dynamic state is streamed as well (evict_first loads and stores).
+// Measured at 65 536 envs (stage_5): level 0 / 1 / 2 = 75.2 / 75.2 / 74.65 us per step.
+#ifndef D2D_L2_HINTS
+#define D2D_L2_HINTS 2
+#endif
+__device__ __forceinline__ uint64_t l2_keep() { uint64_t q; asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(q)); return q; }
+__device__ __forceinline__ uint64_t l2_stream() { uint64_t q; asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(q)); return q; }
+__device__ __forceinline__ double2 ld_keep(const double2 *a)
+{
+#if D2D_L2_HINTS
+    double2 r; asm volatile("ld.global.L2::cache_hint.v2.f64 {%0,%1}, [%2], %3;" : "=d"(r.x), "=d"(r.y) : "l"(a), "l"(l2_keep())); return r;
+#else
+    return *a;
+#endif
+}
+__device__ __forceinline__ double2 ld_stream(const double2 *a)
+{
+#if D2D_L2_HINTS
+    double2 r; asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v2.f64 {%0,%1}, [%2], %3;" : "=d"(r.x), "=d"(r.y) : "l"(a), "l"(l2_stream())); return r;
+#else
+    return *a;
+#endif
+}
+__device__ __forceinline__ double ld_stream(const double *a)
+{
+#if D2D_L2_HINTS
+    double r; asm volatile("ld.global.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(r) : "l"(a), "l"(l2_stream())); return r;
+#else
+    return *a;
+#endif
+}
+__device__ __forceinline__ void st_stream(double2 *a, double2 v)
+{
+#if D2D_L2_HINTS >= 2
+    asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1,%2}, %3;" ::"l"(a), "d"(v.x), "d"(v.y), "l"(l2_stream()) : "memory");
+#else
+    *a = v;
+#endif
+}
+__device__ __forceinline__ double2 ld_state(const double2 *a)
+{
+#if D2D_L2_HINTS >= 2
+    return ld_stream(a);
+#else
+    return *a;
+#endif
+}
+
 struct EnvView {
     const D2dParams *p;
     int64_t i;
@@ -238,13 +312,13 @@ struct EnvView {
     __device__ __forceinline__ int n_obs() const { return nobs; }
     __device__ __forceinline__ double us(int k) const { return us_s ? us_s[k * D2D_US_STRIDE] : p->us[row8(k)]; }
     __device__ __forceinline__ double2 wp(int k) const { return p->wps[row16(k)]; }
-    __device__ __forceinline__ double2 pa(int r) const { return p->pa[row16(r)]; }
-    __device__ __forceinline__ double2 pb(int r) const { return p->pb[row16(r)]; }
-    __device__ __forceinline__ double2 pc(int r) const { return p->pc[row16(r)]; }
+    __device__ __forceinline__ double2 pa(int r) const { return ld_keep(&p->pa[row16(r)]); }
+    __device__ __forceinline__ double2 pb(int r) const { return ld_keep(&p->pb[row16(r)]); }
+    __device__ __forceinline__ double2 pc(int r) const { return ld_keep(&p->pc[row16(r)]); }
     __device__ __forceinline__ void obstacle(int k, double &x, double &y, double &r) const
     {
-        const double2 xy = p->obxy[row16(k)];
-        x = xy.x; y = xy.y; r = p->obr[row8(k)];
+        const double2 xy = ld_stream(&p->obxy[row16(k)]);
+        x = xy.x; y = xy.y; r = ld_stream(&p->obr[row8(k)]);
     }
 };
 
@@ -553,12 +627,12 @@ __device__ __forceinline__ void load_state(const D2dParams &p, int64_t i, EnvSta
 {
 #pragma unroll
     for (int b = 0; b < 3; b++) {
-        const double2 P = p.pos[b * p.np + i], V = p.vel[b * p.np + i], A = p.ang[b * p.np + i];
+        const double2 P = ld_state(&p.pos[b * p.np + i]), V = ld_state(&p.vel[b * p.np + i]), A = ld_state(&p.ang[b * p.np + i]);
         s.px[b] = P.x; s.py[b] = P.y; s.vx[b] = V.x; s.vy[b] = V.y; s.an[b] = A.x; s.om[b] = A.y;
     }
 #pragma unroll
     for (int j = 0; j < 6; j++) {
-        const double2 J = p.jacc[j * p.np + i];
+        const double2 J = ld_state(&p.jacc[j * p.np + i]);
         s.jx[j] = J.x; s.jy[j] = J.y;
     }
     const double2 A = p.acc[i];
@@ -573,12 +647,12 @@ __device__ __forceinline__ void store_bodies(const D2dParams &p, int64_t i, cons
 {
 #pragma unroll
     for (int b = 0; b < 3; b++) {
-        p.pos[b * p.np + i] = make_double2(s.px[b], s.py[b]);
-        p.vel[b * p.np + i] = make_double2(s.vx[b], s.vy[b]);
-        p.ang[b * p.np + i] = make_double2(s.an[b], s.om[b]);
+        st_stream(&p.pos[b * p.np + i], make_double2(s.px[b], s.py[b]));
+        st_stream(&p.vel[b * p.np + i], make_double2(s.vx[b], s.vy[b]));
+        st_stream(&p.ang[b * p.np + i], make_double2(s.an[b], s.om[b]));
     }
 #pragma unroll
-    for (int j = 0; j < 6; j++) p.jacc[j * p.np + i] = make_double2(s.jx[j], s.jy[j]);
+    for (int j = 0; j < 6; j++) st_stream(&p.jacc[j * p.np + i], make_double2(s.jx[j], s.jy[j]));
 }
 
 __device__ __forceinline__ void store_scalars(const D2dParams &p, int64_t i, const EnvState &s)
@@ -1015,6 +1089,21 @@ __device__ __forceinline__ void path_point_and_gradient(const V &v, double u, do
 // generate_obstacles_around_path (obstacles.py:58-89): rejection sampler.  The offset direction
 // (cos, sin)(atan2(gy, gx) - pi/2) is (gy, -gx)/|g|, evaluated without the transcendental round trip
 // (differs from the reference's value by rounding only; reset parity tolerance 1e-7 px).
+// One attempt from its three variates (u ~ U(0.2L, 0.9L), offset ~ N(mean, sd), radius ~ U(10, 50)): the candidate
+// circle and whether obstacles.py:71-86 keeps it.  Shared by the serial and the warp-cooperative sampler, so that
+// both produce the same obstacles bit for bit.
+__device__ __forceinline__ bool obstacle_attempt(EnvView &ev, double u_obs, double dist, double size, bool on_path,
+                                                 double &ox, double &oy)
+{
+    double gx, gy, x, y;
+    path_point_and_gradient(ev, u_obs, x, y, gx, gy);
+    if (on_path) { ox = x; oy = y; return true; }
+    const double inv_g = rsqrt(gx * gx + gy * gy);
+    ox = x + dist * (gy * inv_g); oy = y + dist * (-gx * inv_g);
+    const double ddx = ox - x, ddy = oy - y;
+    return sqrt(ddx * ddx + ddy * ddy) > size + 10.0;
+}
+
 __device__ __forceinline__ int sample_obstacles(const D2dParams &p, EnvView &ev, ResetRng &rng, int slot, int count,
                                                 double mean, double sd, bool on_path)
 {
@@ -1025,22 +1114,57 @@ __device__ __forceinline__ int sample_obstacles(const D2dParams &p, EnvView &ev,
         const double u_obs = rng.uniform(0.20 * L, 0.90 * L);
         const double dist = rng.normal(mean, sd);
         const double size = rng.uniform(10.0, 50.0);
-        double gx, gy, x, y;
-        path_point_and_gradient(ev, u_obs, x, y, gx, gy);
-        if (on_path) {
-            p.obxy[ev.row16(slot)] = make_double2(x, y);
-            p.obr[ev.row8(slot)] = size;
-            slot++; made++;
-            continue;
-        }
-        const double inv_g = rsqrt(gx * gx + gy * gy);
-        const double ox = x + dist * (gy * inv_g), oy = y + dist * (-gx * inv_g);
-        const double ddx = ox - x, ddy = oy - y;
-        if (sqrt(ddx * ddx + ddy * ddy) > size + 10.0) {
+        double ox, oy;
+        if (obstacle_attempt(ev, u_obs, dist, size, on_path, ox, oy)) {
             p.obxy[ev.row16(slot)] = make_double2(ox, oy);
             p.obr[ev.row8(slot)] = size;
             slot++; made++;
         }
+    }
+    return slot;
+}
+
+// The same sampler run by a whole warp for ONE environment (off-path obstacles): lane l evaluates attempt a0 + l,
+// whose four variates are draws draw0 + 4 (a0 + l) .. + 3 of the env's counter-based stream; the accepted attempts
+// are kept in attempt order until `count` circles exist, exactly like the serial loop (which stops drawing right
+// after the attempt that completes the count).  All arguments are warp-uniform.  Returns the new slot count and,
+// through `draws_used`, how far the serial stream has advanced.  The obstacle rejection loop has a data-dependent
+// trip count (~1.4 attempts per circle, up to 31 circles) and was the longest chain of the refill roles.
+__device__ __noinline__ int sample_obstacles_coop(const D2dParams &p, EnvView &ev, const ResetRng &rng, uint32_t draw0,
+                                                     int slot, int count, double mean, double sd, uint32_t &draws_used)
+{
+    const double L = ev.us(ev.n_wps() - 1);
+    const int lane = threadIdx.x & 31;
+    int made = 0;
+    uint32_t a0 = 0;
+    draws_used = 0;
+    while (made < count && slot < D2D_MAX_OBS_ENV && a0 < 4096u) {
+        const uint32_t d = draw0 + 4u * (a0 + (uint32_t)lane);
+        const double u_obs = uniform_from(rng.u01_at(d), 0.20 * L, 0.90 * L);
+        const double dist = normal_from(rng.u01_at(d + 1), rng.u01_at(d + 2), mean, sd);
+        const double size = uniform_from(rng.u01_at(d + 3), 10.0, 50.0);
+        double ox, oy;
+        const bool ok = obstacle_attempt(ev, u_obs, dist, size, false, ox, oy);
+        const unsigned acc = __ballot_sync(0xffffffffu, ok);
+        const int need = min(count - made, D2D_MAX_OBS_ENV - slot);
+        const int rank = __popc(acc & ((1u << lane) - 1u));
+        if (ok && rank < need) {
+            p.obxy[ev.row16(slot + rank)] = make_double2(ox, oy);
+            p.obr[ev.row8(slot + rank)] = size;
+        }
+        const int got = __popc(acc);
+        if (got >= need) {
+            // the attempt that completed the count: the need-th accepted lane of this batch
+            unsigned m = acc;
+            for (int k = 1; k < need; k++) m &= m - 1;
+            const int last = __ffs(m) - 1;
+            slot += need; made += need;
+            draws_used = 4u * (a0 + (uint32_t)last + 1u);
+            return slot;
+        }
+        slot += got; made += got;
+        a0 += 32u;
+        draws_used = 4u * a0;
     }
     return slot;
 }
@@ -1054,8 +1178,17 @@ struct ResetOut {
     int n_obs;
 };
 
+// Off-path obstacles the caller will draw itself, with the whole warp (sample_obstacles_coop), instead of the lane:
+// `count` circles starting at draw `draw0` of the episode's stream, then (stage_5) one on-path circle.
+struct ObstaclePlan {
+    int count;
+    uint32_t draw0;
+    int then_on_path;
+};
+
 template <bool PER_ENV>
-__device__ __noinline__ ResetOut reset_env(const D2dParams &p, int64_t i, int episode, int par, double *us_s)
+__device__ __noinline__ ResetOut reset_env(const D2dParams &p, int64_t i, int episode, int par, double *us_s,
+                                           ObstaclePlan *plan = nullptr)
 {
     const D2dConst &c = p.c;
     ResetRng rng((uint32_t)(c.env_id_base + i), (uint32_t)episode, c.seed_lo, c.seed_hi);
@@ -1119,7 +1252,10 @@ __device__ __noinline__ ResetOut reset_env(const D2dParams &p, int64_t i, int ep
         sx = rng.uniform(100.0, c.W - 100.0);
         sy = rng.uniform(100.0, c.H - 100.0);
     } else if (c.stage == 3) {                                    // env:334-347
-        if (rng.u01() < c.spawn_chance) n_obs = sample_obstacles(p, ev, rng, 0, 1, 0.0, 100.0, false);
+        if (rng.u01() < c.spawn_chance) {
+            if (plan) { plan->count = 1; plan->draw0 = rng.position(); plan->then_on_path = 0; }
+            else n_obs = sample_obstacles(p, ev, rng, 0, 1, 0.0, 100.0, false);
+        }
     } else if (c.stage == 4) {                                    // env:348-361
         if (rng.u01() < c.spawn_chance) n_obs = sample_obstacles(p, ev, rng, 0, 1, 0.0, 0.0, true);
     } else if (c.stage == 5) {                                    // env:362-372
@@ -1130,8 +1266,12 @@ __device__ __noinline__ ResetOut reset_env(const D2dParams &p, int64_t i, int ep
             int want = (int)ceil(nn);                             // `while num_obstacles < n` with float n
             if (want < 0) want = 0;                               // nn == -3 exactly
             if (want > D2D_MAX_OBS_ENV - 1) want = D2D_MAX_OBS_ENV - 1;
-            n_obs = sample_obstacles(p, ev, rng, 0, want, 0.0, 100.0, false);
-            n_obs = sample_obstacles(p, ev, rng, n_obs, 1, 0.0, 0.0, true);
+            if (plan && want > 0) {
+                plan->count = want; plan->draw0 = rng.position(); plan->then_on_path = 1;
+            } else {
+                n_obs = sample_obstacles(p, ev, rng, 0, want, 0.0, 100.0, false);
+                n_obs = sample_obstacles(p, ev, rng, n_obs, 1, 0.0, 0.0, true);
+            }
         }
     }
     return ResetOut{sx, sy, sa, n_obs};
