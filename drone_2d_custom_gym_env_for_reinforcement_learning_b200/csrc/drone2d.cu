@@ -219,9 +219,9 @@ __global__ void __launch_bounds__(D2D_BLOCK, D2D_MIN_BLOCKS) d2d_step_kernel(con
     const long long t_start = clock64();
     int *qa = p.queue, *qb = p.queue + 3 * p.np, *qb_tgt = p.queue + 6 * p.np;
     int *qa_cnt = p.qcount, *qb_cnt = p.qcount + 3;
-    if ((int)blockIdx.x < 2 * p.refill_blocks) {
-        const int total = p.refill_blocks * D2D_BLOCK, n_warps = total / 32;
+    if ((int)blockIdx.x < p.refill_blocks + p.observe_blocks) {
         const bool sample_role = (int)blockIdx.x < p.refill_blocks;
+        const int total = (sample_role ? p.refill_blocks : p.observe_blocks) * D2D_BLOCK, n_warps = total / 32;
         const int g = (sample_role ? blockIdx.x : blockIdx.x - p.refill_blocks) * D2D_BLOCK + tid;
         const int first = (g & 31) * n_warps + (g >> 5);        // task dealt to (warp, lane): lane-major over warps
         if (sample_role) {
@@ -241,7 +241,7 @@ __global__ void __launch_bounds__(D2D_BLOCK, D2D_MIN_BLOCKS) d2d_step_kernel(con
         return;
     }
 
-    const int64_t blk = (int64_t)blockIdx.x - 2 * p.refill_blocks;
+    const int64_t blk = (int64_t)blockIdx.x - (p.refill_blocks + p.observe_blocks);
     const int64_t i = blk * D2D_BLOCK + tid;
     const bool valid = i < p.n;
     const unsigned vmask = __ballot_sync(0xffffffffu, valid);       // the lanes of this warp that own an environment
@@ -300,6 +300,46 @@ __global__ void __launch_bounds__(D2D_BLOCK, D2D_MIN_BLOCKS) d2d_step_kernel(con
         const bool hit = scan_obstacles(v, c, s.px[0], s.py[0], rc0, rs0, true, nr);
         if (hit) s.flags |= D2D_F_COLLIDED;                         // begin callback, env:17-19
 
+        // end conditions, known before the search (see end_bits_of)
+        int end_bits;
+        {
+            const double2 tgt = v.wp(v.n_wps() - 1);
+            end_bits = end_bits_of(c, s, div_const(s.an[0], D2D_PI, c.r_pi), m1to1(tgt.x - s.px[0], 0.0, c.W, c.r_W),
+                                   m1to1(tgt.y - s.py[0], 0.0, c.H, c.r_H));
+        }
+        const bool will_swap = (end_bits != 0 || (s.flags & D2D_F_DONE)) && p.auto_reset;   // = r.done below
+        if (will_swap) {
+            // ask the next step's refill blocks for the episode after the next one, and start pulling the
+            // staged episode (spawn pose, first observation) into the L2: both round trips overlap the search
+            qa[(int64_t)q_write * p.np + atomicAdd(&qa_cnt[q_write], 1)] = (int)i;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(&p.stg_meta[i]));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(&p.stg_xy[i]));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(&p.stg_an[i]));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.stg_obs + i * D2D_OBS_DIM));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.stg_obs + i * D2D_OBS_DIM + D2D_OBS_DIM - 1));
+        }
+        if (PER_ENV) {
+            // ... and its staged tables, by the whole warp (the copy at the end of the kernel reads them)
+            unsigned m = __ballot_sync(vmask, will_swap);
+            const uint32_t np32 = (uint32_t)p.np;
+            while (m) {
+                const int src = __ffs(m) - 1;
+                m &= m - 1;
+                const uint32_t e = (uint32_t)(blk * D2D_BLOCK + (tid & ~31) + src);
+#pragma unroll
+                for (int r = 0; r < 2; r++) {
+                    const int t = lane + 32 * r;
+                    if (t < 4 * c.n_wps) {
+                        const double2 *a = (t & 3) == 0 ? p.wps : ((t & 3) == 1 ? p.pa : ((t & 3) == 2 ? p.pb : p.pc));
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(a + p.stg_off16 + (uint32_t)(t >> 2) * np32 + e));
+                    }
+                    if (t < c.n_wps) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.us + p.stg_off8 + (uint32_t)t * np32 + e));
+                    else if (t - c.n_wps < D2D_MAX_OBS_ENV) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.obr + p.stg_off8 + (uint32_t)(t - c.n_wps) * np32 + e));
+                }
+                if (lane < D2D_MAX_OBS_ENV) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.obxy + p.stg_off16 + (uint32_t)lane * np32 + e));
+            }
+        }
+
         double *o64 = p.obs64 ? p.obs64 + i * D2D_OBS_DIM : nullptr;
         auto put = [&](int j, double val) {
             row[j] = (float)val;
@@ -328,7 +368,7 @@ __global__ void __launch_bounds__(D2D_BLOCK, D2D_MIN_BLOCKS) d2d_step_kernel(con
         const long long t_obs = clock64();
 
         StepResult r;
-        reward_and_done(c, s, ax, v.n_obs() > 0, rs0, r);
+        reward_and_done(c, s, ax, v.n_obs() > 0, rs0, end_bits, r);
         p.reward[i] = (float)r.reward;
         p.done[i] = r.done ? 1 : 0;
         if (p.info && (r.done || !p.info_done_only)) {
@@ -401,8 +441,6 @@ __global__ void __launch_bounds__(D2D_BLOCK, D2D_MIN_BLOCKS) d2d_step_kernel(con
                 spawn(s, c, nx, ny, na);
                 s.flags = new_flags; s.episode = next_ep; s.n_obs = n_obs;
                 store_bodies(p, i, s);
-                // ask the next step's refill blocks for episode next_ep + 1
-                qa[(int64_t)q_write * p.np + atomicAdd(&qa_cnt[q_write], 1)] = (int)i;
             }
         }
         store_scalars(p, i, s);
@@ -816,6 +854,10 @@ int d2d_create(const d2d_config *cfg, int64_t n_envs, int64_t env_id_base, uint6
             cudaGetLastError();
         }
         p.refill_blocks = want < 1 ? 1 : want;
+        p.observe_blocks = p.refill_blocks;
+        // tuning overrides (tools/refill_split_probe.py)
+        if (const char *sb = getenv("D2D_SAMPLE_BLOCKS")) { const int v = atoi(sb); if (v >= 1) p.refill_blocks = v; }
+        if (const char *ob = getenv("D2D_OBSERVE_BLOCKS")) { const int v = atoi(ob); if (v >= 1) p.observe_blocks = v; }
     }
     if (L.per_env_tables) {
         p.us = (double *)(base + L.off_us); p.wps = (double2 *)(base + L.off_wps);
@@ -1006,7 +1048,7 @@ int d2d_step(d2d_env *e, const float *actions_dev, float *obs_dev, float *reward
     p.actions = actions_dev; p.obs = obs_dev; p.reward = reward_dev; p.done = done_dev;
     p.terminal_obs = terminal_obs_dev; p.auto_reset = auto_reset; p.step_index = e->step_index++;
     cudaStream_t st = (cudaStream_t)stream;
-    const int grid = grid_for(p.n, D2D_BLOCK) + 2 * p.refill_blocks;
+    const int grid = grid_for(p.n, D2D_BLOCK) + p.refill_blocks + p.observe_blocks;
     cudaLaunchConfig_t lc = {};
     lc.gridDim = dim3((unsigned)grid); lc.blockDim = dim3(D2D_BLOCK); lc.dynamicSmemBytes = 0; lc.stream = st;
     cudaLaunchAttribute attr[2];

@@ -972,14 +972,30 @@ struct StepResult {
     bool done;
 };
 
+// The four end conditions (env:543-570) depend on the pose, the step count and the collision flag only: they
+// are known right after the rigid-body step and the obstacle scan, i.e. BEFORE the closest-point search.  The
+// step kernel evaluates them there (so that a lane whose episode ends can announce it to the refill queue and
+// pull its staged episode towards the L2 while the search runs) and hands the bits to reward_and_done, which
+// uses them as they are.  o3, o4, o5 = observation entries 3, 4, 5 (same expressions as observe()).
+__device__ __forceinline__ int end_bits_of(const D2dConst &c, const EnvState &s, double o3, double o4, double o5)
+{
+    const double alpha = o3 * D2D_PI;
+    const double tdx = invm1to1(o4, 0.0, c.W), tdy = invm1to1(o5, 0.0, c.H);
+    int bits = 0;
+    if (s.flags & D2D_F_COLLIDED) bits |= 1;
+    if (fabs(tdx) < c.reach_end_radius && fabs(tdy) < c.reach_end_radius) bits |= 2;
+    if (fabs(alpha) >= c.AA_angle) bits |= 8;
+    if (s.steps == c.n_steps) bits |= 4;
+    return bits;
+}
+
 __device__ __forceinline__ void reward_and_done(const D2dConst &c, EnvState &s, const ObsAux &o, bool has_obstacles,
-                                                double sin_alpha, StepResult &r)
+                                                double sin_alpha, int bits, StepResult &r)
 {
     const double W = c.W, H = c.H;
     // env:423-445: decode the observation back to physical units
     const double vel_x = invm1to1(o.o0, -1330.0, 1330.0), vel_y = invm1to1(o.o1, -1330.0, 1330.0);
     const double alpha = o.o3 * D2D_PI;
-    const double tdx = invm1to1(o.o4, 0.0, W), tdy = invm1to1(o.o5, 0.0, H);
     const double pos_x = invm1to1(o.o6, 0.0, W), pos_y = invm1to1(o.o7, 0.0, H);
     const double cpx = invm1to1(o.o19, 0.0, W), cpy = invm1to1(o.o20, 0.0, H);
     // env:435,444-445,482 decode velocity / look-ahead / obstacle angles with arctan2 only to take differences of
@@ -1015,16 +1031,14 @@ __device__ __forceinline__ void reward_and_done(const D2dConst &c, EnvState &s, 
     const double cos_vel_LA = o.o24 * o.o18 + o.o23 * o.o17;             // cos(look-ahead angle - velocity angle)
     const double r_PP = clipd(cos_vel_LA * (velocity * c.PP_vel_scale), c.PP_rew_min, c.PP_rew_max);
     // env:543-570
-    int bits = 0;
     double r_coll = 0.0, r_end = 0.0, r_AA = 0.0;
-    if (s.flags & D2D_F_COLLIDED) { r_coll = c.rew_collision; bits |= 1; }
-    if (fabs(tdx) < c.reach_end_radius && fabs(tdy) < c.reach_end_radius) { r_end = c.rew_reach_end; bits |= 2; }
+    if (bits & 1) r_coll = c.rew_collision;
+    if (bits & 2) r_end = c.rew_reach_end;
     // env:557-565: np.sin(alpha) of the decoded angle; the sine of the frame angle is already known from the rigid-body
     // step (the decode alpha/pi*pi moves the angle by an ulp at most: rounding-level difference)
     if (alpha > c.AA_band) r_AA = -sin_alpha;
     if (alpha < -c.AA_band) r_AA = sin_alpha;
-    if (fabs(alpha) >= c.AA_angle) { r_AA = c.rew_AA; bits |= 8; }
-    if (s.steps == c.n_steps) bits |= 4;
+    if (bits & 8) r_AA = c.rew_AA;
     // env:572
     r.reward = r_AA + r_PA * lambda_PA + r_PP + r_coll + r_CA * lambda_CA + r_end;
     r.r_CA = r_CA * lambda_CA; r.r_PA = r_PA * lambda_PA; r.r_PP = r_PP;

@@ -170,7 +170,8 @@ struct D2dParams {
     int4 *stg_meta;
     float *stg_obs;
     int *queue, *qcount;
-    int refill_blocks;         // leading blocks of the step grid that prefetch episodes (per stage)
+    int refill_blocks;         // leading blocks of the step grid that sample staged episodes (sample role)
+    int observe_blocks;        // blocks after them that compute the staged episodes' first observation (observe role)
     const D2dSharedTables *shared;
     // I/O of one step
     const float *actions;
