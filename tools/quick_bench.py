@@ -47,5 +47,6 @@ st = env.episode_stats()
 print(json.dumps({"lib": os.path.basename(os.environ.get("D2D_LIB", "default")), "envs": E, "scenario": scen,
                   "early_us": round(early, 1), "steady_us": round(steady, 1),
                   "steady_Msteps_s": round(E / steady, 1), "mean_ep_len": round(st["env_steps"] / max(st["episodes"], 1), 1),
+                  "episodes": int(st["episodes"]), "inlane_resets": int(st["inlane_resets"]),
                   "kcyc_early(max,mean)": {k: (v["max"] // 1000, v["mean"] // 1000) for k, v in rc_early.items()},
                   "kcyc_steady(max,mean)": {k: (v["max"] // 1000, v["mean"] // 1000) for k, v in rc_steady.items()}}))
