@@ -264,6 +264,12 @@ __global__ void __launch_bounds__(D2D_BLOCK, D2D_MIN_BLOCKS) d2d_step_kernel(con
                 asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(p.us + base + (uint32_t)k * (uint32_t)p.np));
 #endif
             }
+            // ... and the path points of the search's three opening evaluations (brent_opening) go into rows 0..3 of
+            // the lane's cursor column, which the cursor itself only fills at its first locate() (fourth evaluation)
+            for (int k = 0; k < D2D_HINTS; k++) {
+                const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&s_coef[k * D2D_BLOCK + tid]);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(p.hint + base + (uint32_t)k * (uint32_t)p.np));
+            }
             asm volatile("cp.async.commit_group;" ::: "memory");
         }
 
@@ -347,7 +353,7 @@ __global__ void __launch_bounds__(D2D_BLOCK, D2D_MIN_BLOCKS) d2d_step_kernel(con
         };
         ObsAux ax;
         const long long t_scan = clock64();
-        observe(v, c, s, rc0, rs0, nr, put, ax, &s_coef[tid]);
+        observe(v, c, s, rc0, rs0, nr, put, ax, &s_coef[tid], PER_ENV);
         // The warp's 32 observation rows are contiguous in the output ([N][27] float32): store them now, coalesced,
         // instead of at block end -- when the outputs live in mapped host memory (d2d_step_host) the PCIe writes
         // then start while reward / swap and the block's slower warps are still running.
@@ -482,6 +488,9 @@ __global__ void __launch_bounds__(D2D_BLOCK, D2D_MIN_BLOCKS) d2d_step_kernel(con
                 else if (u < nob) v8[r] = p.obr[p.stg_off8 + (uint32_t)u * np32 + e];
             }
             if (lane < nob) vob = p.obxy[p.stg_off16 + (uint32_t)lane * np32 + e];
+            double2 vh;
+            if (lane < D2D_HINTS) vh = p.hint[p.stg_off16 + (uint32_t)lane * np32 + e];
+            if (lane < D2D_HINTS) p.hint[(uint32_t)lane * np32 + e] = vh;
 #pragma unroll
             for (int r = 0; r < 2; r++) {
                 const int t = lane + 32 * r;
@@ -624,6 +633,8 @@ __global__ void d2d_pack_tables_kernel(const D2dParams p, double *wps, double *u
         int4 m = p.meta[i];
         m.w = n_obs[i];
         p.meta[i] = m;
+        const EnvView ev{&p, i, 0, 0, nullptr};
+        store_hints(p, ev);                                      // the injected path's opening points
     }
 }
 
@@ -862,6 +873,7 @@ int d2d_create(const d2d_config *cfg, int64_t n_envs, int64_t env_id_base, uint6
     if (L.per_env_tables) {
         p.us = (double *)(base + L.off_us); p.wps = (double2 *)(base + L.off_wps);
         p.pa = (double2 *)(base + L.off_pa); p.pb = (double2 *)(base + L.off_pb); p.pc = (double2 *)(base + L.off_pc);
+        p.hint = (double2 *)(base + L.off_hint);
         p.obxy = (double2 *)(base + L.off_obxy); p.obr = (double *)(base + L.off_obr);
         p.stg_off8 = (uint32_t)(L.stg_delta / 8); p.stg_off16 = (uint32_t)(L.stg_delta / 16);
     }

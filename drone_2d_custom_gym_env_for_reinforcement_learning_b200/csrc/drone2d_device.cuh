@@ -526,8 +526,51 @@ struct PathCursor {
 // is one more evaluation at the minimiser after the loop (4 selects per trip cheaper than
 // carrying the best point through the loop).
 // Every lane runs its own iteration count (typically 10-47).
+// The OPENING of that search does not depend on the query point: the first evaluation is at
+// x0 = a + g (b - a), the second (e = 0: a golden-section step) at x1 = x0 + g (b - x0), and the third is a
+// golden-section step again -- with three evaluations in hand two of scipy's three points coincide, p = q = 0 and
+// the parabolic step is rejected -- from x1 into (x0, b) if the second value was not worse, from x0 into (a, x1) if it
+// was.  Four abscissae per PATH, computed here with the search's own operations; their path points are stored with
+// the episode's tables (D2dParams::hint), so the three opening evaluations of every search of the episode -- the ones
+// that jump across the whole path and each miss the cursor's cached region (a DRAM round trip for the warp) -- need
+// no table access at all.
+__device__ __forceinline__ void brent_opening(double L, double u[D2D_HINTS])
+{
+    const double xatol_3 = 1e-6 / 3.0, sqrt_eps = 1.4832396974191326e-08, golden_mean = 0.3819660112501051;
+    const double a = -10.0, b = S::add(L, 10.0);
+    auto golden_step = [&](double lo, double hi, double xf) {
+        const double xm = S::mul(0.5, S::add(lo, hi));
+        const double tol1 = S::add(S::mul(sqrt_eps, fabs(xf)), xatol_3);
+        const double e = (xf >= xm) ? S::sub(lo, xf) : S::sub(hi, xf);
+        const double rat = S::mul(golden_mean, e);
+        const double mag = max_f(fabs(rat), tol1);
+        return S::add(xf, (rat < 0.0) ? -mag : mag);
+    };
+    u[0] = S::add(a, S::mul(golden_mean, S::sub(b, a)));
+    u[1] = golden_step(a, b, u[0]);
+    u[2] = golden_step(u[0], b, u[1]);      // f(x1) <= f(x0): bracket (x0, b), best point x1
+    u[3] = golden_step(a, u[1], u[0]);      // f(x1) >  f(x0): bracket (a, x1), best point x0
+}
+
+// Path points of the opening, written next to the tables they were evaluated on (reset / staging / d2d_set_tables).
 template <class V>
-__device__ __forceinline__ double closest_u(PathCursor<V> &pc, double px, double py, int &nfev, double &bx, double &by)
+__device__ __forceinline__ void store_hints(const D2dParams &p, const V &v)
+{
+    double u[D2D_HINTS];
+    brent_opening(v.us(v.n_wps() - 1), u);
+#pragma unroll
+    for (int k = 0; k < D2D_HINTS; k++) {
+        double x, y;
+        path_eval(v, u[k], x, y);
+        p.hint[v.row16(k)] = make_double2(x, y);
+    }
+}
+
+// `hinted`: the cursor's column holds the D2D_HINTS opening points in its rows 0..3 (they are consumed before the
+// cursor's first locate() overwrites the column).
+template <class V>
+__device__ __forceinline__ double closest_u(PathCursor<V> &pc, double px, double py, int &nfev, double &bx, double &by,
+                                            bool hinted = false)
 {
     const double xatol_3 = 1e-6 / 3.0;
     const int maxfun = 500;
@@ -541,7 +584,8 @@ __device__ __forceinline__ double closest_u(PathCursor<V> &pc, double px, double
     double fx, ffulc, fnfc;
     {
         double ex, ey;
-        pc.eval(x, ex, ey);
+        if (hinted) { const double2 h = pc.template ld<0>(); ex = h.x; ey = h.y; }
+        else pc.eval(x, ex, ey);
         const double dx = S::sub(ex, px), dy = S::sub(ey, py);
         fx = ffulc = fnfc = S::sqrt(S::fma(dy, dy, S::mul(dx, dx)));
     }
@@ -585,7 +629,15 @@ __device__ __forceinline__ double closest_u(PathCursor<V> &pc, double px, double
 
         // objective: np.linalg.norm(path(x) - pos) = sqrt(fma(dy, dy, dx*dx))  (BLAS ddot, predef_path.py:246)
         double ex, ey;
-        pc.eval(x, ex, ey);
+        if (hinted && num < 3) {
+            // second and third evaluation (see brent_opening): after the second one the best point is x1 > nfc = x0
+            // if it was not worse, x0 < nfc = x1 if it was
+            const double2 h1 = pc.template ld<1>(), h2 = pc.template ld<2>(), h3 = pc.template ld<3>();
+            const double2 h = (num == 1) ? h1 : ((xf > nfc) ? h2 : h3);
+            ex = h.x; ey = h.y;
+        } else {
+            pc.eval(x, ex, ey);
+        }
         const double dx = S::sub(ex, px), dy = S::sub(ey, py);
         const double fu = S::sqrt(S::fma(dy, dy, S::mul(dx, dx)));
         num += 1;
@@ -894,7 +946,7 @@ struct ObsAux {
 
 template <class V, class Put>
 __device__ __forceinline__ void observe(const V &v, const D2dConst &c, EnvState &s, double rc0, double rs0,
-                                        const Nearest &nr, Put put, ObsAux &ax, double2 *coef)
+                                        const Nearest &nr, Put put, ObsAux &ax, double2 *coef, bool hinted = false)
 {
     const double W = c.W, H = c.H;
     const double x = s.px[0], y = s.py[0], alpha = s.an[0];
@@ -936,7 +988,7 @@ __device__ __forceinline__ void observe(const V &v, const D2dConst &c, EnvState 
     int nfev;
     PathCursor<V> pc(v, coef);
     double cx, cy;
-    const double u = closest_u(pc, x, y, nfev, cx, cy);
+    const double u = closest_u(pc, x, y, nfev, cx, cy, hinted);
     ax.o19 = m1to1(cx, 0.0, W, c.r_W); ax.o20 = m1to1(cy, 0.0, H, c.r_H);
     put(19, ax.o19); put(20, ax.o20);
     ax.u_star = u; ax.nfev = nfev;
@@ -1259,6 +1311,7 @@ __device__ __noinline__ ResetOut reset_env(const D2dParams &p, int64_t i, int ep
         xa = xb; ya = yb; xb = nx; yb = ny;
         u_prev2 = u_prev; u_prev = u_cur;
     }
+    store_hints(p, ev);                                           // opening points of this path's searches
     double sx = x0, sy = y0;                                      // env:320-321
     const double sa = rng.uniform(-D2D_PI / 4, D2D_PI / 4);       // env:322
     int n_obs = 0;

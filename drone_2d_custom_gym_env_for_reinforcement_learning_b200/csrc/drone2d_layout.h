@@ -44,6 +44,7 @@
 #include "../../include/drone2d.h"
 
 // Launch geometry of every per-env kernel (one lane per environment).
+#define D2D_HINTS 4   // opening of the bounded Brent search: x0, x1, x2 (second point better), x2 (second point worse)
 #ifndef D2D_BLOCK
 #define D2D_BLOCK 128
 #endif
@@ -62,7 +63,7 @@ struct D2dLayout {
     int64_t np;         // padded to a multiple of 32 (row stride)
     size_t off_pos, off_vel, off_ang, off_jacc, off_acc, off_meta, off_last;
     size_t off_stg_xy, off_stg_an, off_stg_meta, off_stg_obs, off_queue, off_qcount;
-    size_t off_us, off_wps, off_pa, off_pb, off_pc, off_obxy, off_obr;
+    size_t off_us, off_wps, off_pa, off_pb, off_pc, off_hint, off_obxy, off_obr;
     size_t bytes;
     size_t hot_bytes;      // leading bytes touched by every step (state + live us/rows)
     size_t stg_delta;      // byte distance from a live per-env table to its staged copy
@@ -86,7 +87,7 @@ static inline void d2d_make_layout(D2dLayout *L, int64_t n, int per_env_tables)
     L->off_jacc = take(6 * np * 16);
     L->off_acc = take(np * 16);
     L->off_meta = take(np * 16);
-    L->off_us = L->off_wps = L->off_pa = L->off_pb = L->off_pc = L->off_obxy = L->off_obr = 0;
+    L->off_us = L->off_wps = L->off_pa = L->off_pb = L->off_pc = L->off_hint = L->off_obxy = L->off_obr = 0;
     L->stg_delta = 0;
     size_t live_begin = o;
     if (per_env_tables) {
@@ -94,6 +95,7 @@ static inline void d2d_make_layout(D2dLayout *L, int64_t n, int per_env_tables)
         L->off_pa = take((size_t)D2D_MAX_WPS * np * 16);
         L->off_pb = take((size_t)D2D_MAX_WPS * np * 16);
         L->off_pc = take((size_t)D2D_MAX_WPS * np * 16);
+        L->off_hint = take((size_t)D2D_HINTS * np * 16);
     }
     L->hot_bytes = o;
     if (per_env_tables) {
@@ -164,6 +166,7 @@ struct D2dParams {
     int4 *meta;
     double *us;
     double2 *wps, *pa, *pb, *pc, *obxy;
+    double2 *hint;                  // [D2D_HINTS][np]: path points of the opening evaluations of every closest-point search
     double *obr;
     uint32_t stg_off8, stg_off16;   // element offsets (8- / 16-byte elements) from a live table to its staged copy
     double2 *stg_xy, *stg_an;
