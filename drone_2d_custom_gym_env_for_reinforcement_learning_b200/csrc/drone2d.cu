@@ -266,7 +266,7 @@ __global__ void __launch_bounds__(D2D_BLOCK, D2D_MIN_BLOCKS) d2d_step_kernel(con
             }
             // ... and the path points of the search's three opening evaluations (brent_opening) go into rows 0..3 of
             // the lane's cursor column, which the cursor itself only fills at its first locate() (fourth evaluation)
-            for (int k = 0; k < D2D_HINTS; k++) {
+            for (int k = 0; k < (p.use_hints ? D2D_HINTS : 0); k++) {
                 const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&s_coef[k * D2D_BLOCK + tid]);
                 asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(p.hint + base + (uint32_t)k * (uint32_t)p.np));
             }
@@ -353,7 +353,7 @@ __global__ void __launch_bounds__(D2D_BLOCK, D2D_MIN_BLOCKS) d2d_step_kernel(con
         };
         ObsAux ax;
         const long long t_scan = clock64();
-        observe(v, c, s, rc0, rs0, nr, put, ax, &s_coef[tid], PER_ENV);
+        observe(v, c, s, rc0, rs0, nr, put, ax, &s_coef[tid], PER_ENV && p.use_hints);
         // The warp's 32 observation rows are contiguous in the output ([N][27] float32): store them now, coalesced,
         // instead of at block end -- when the outputs live in mapped host memory (d2d_step_host) the PCIe writes
         // then start while reward / swap and the block's slower warps are still running.
@@ -869,6 +869,8 @@ int d2d_create(const d2d_config *cfg, int64_t n_envs, int64_t env_id_base, uint6
         // tuning overrides (tools/refill_split_probe.py)
         if (const char *sb = getenv("D2D_SAMPLE_BLOCKS")) { const int v = atoi(sb); if (v >= 1) p.refill_blocks = v; }
         if (const char *ob = getenv("D2D_OBSERVE_BLOCKS")) { const int v = atoi(ob); if (v >= 1) p.observe_blocks = v; }
+        p.use_hints = 1;
+        if (const char *uh = getenv("D2D_SEARCH_HINTS")) p.use_hints = atoi(uh) != 0;   // tests: hinted == unhinted, bit for bit
     }
     if (L.per_env_tables) {
         p.us = (double *)(base + L.off_us); p.wps = (double2 *)(base + L.off_wps);

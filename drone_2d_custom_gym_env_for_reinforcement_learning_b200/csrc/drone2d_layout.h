@@ -175,6 +175,7 @@ struct D2dParams {
     int *queue, *qcount;
     int refill_blocks;         // leading blocks of the step grid that sample staged episodes (sample role)
     int observe_blocks;        // blocks after them that compute the staged episodes' first observation (observe role)
+    int use_hints;             // 1: the search's opening evaluations come from `hint` (0 only for the A/B test: same bits)
     const D2dSharedTables *shared;
     // I/O of one step
     const float *actions;

@@ -179,3 +179,34 @@ def test_state_and_table_round_trip(pkg):
     for k in tb2:
         assert np.array_equal(got[k], tb2[k]), k
     env.close()
+
+
+def test_search_opening_table_changes_no_bit(pkg, monkeypatch):
+    """The path points of the search's three opening evaluations are stored with the episode's tables
+    (csrc/drone2d_device.cuh: brent_opening / store_hints).  With the table switched off the search evaluates the
+    path itself, as scipy does: observations (float64 tap, incl. u* and nfev in the info rows), rewards and dones of
+    two otherwise identical batches must agree bit for bit over hundreds of steps and auto-resets."""
+    import torch
+    n, steps = 4096, 300
+    envs = []
+    for hints in ("1", "0"):
+        monkeypatch.setenv("D2D_SEARCH_HINTS", hints)
+        e = pkg.Drone2dVecEnv(n, seed=5, info_mode="full", mode="curriculum", scenario="stage_5")
+        e.reset_device()
+        envs.append(e)
+    monkeypatch.delenv("D2D_SEARCH_HINTS")
+    g = torch.Generator(device=envs[0].device)
+    g.manual_seed(2)
+    dones = 0
+    for k in range(steps):
+        act = torch.rand((n, 2), device=envs[0].device, generator=g) * 2 - 1
+        outs = []
+        for e in envs:
+            o, r, d = e.step_device(act)
+            outs.append((o.clone(), r.clone(), d.clone(), e.obs64.clone(), e.info.clone()))
+        for a, b in zip(outs[0], outs[1]):
+            assert torch.equal(a, b), k
+        dones += int(outs[0][2].sum())
+    assert dones > n            # every env went through several auto-resets (staged tables + their opening points)
+    for e in envs:
+        e.close()
