@@ -270,6 +270,10 @@ __global__ void __launch_bounds__(D2D_BLOCK, D2D_MIN_BLOCKS) d2d_step_kernel(con
                 const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&s_coef[k * D2D_BLOCK + tid]);
                 asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(p.hint + base + (uint32_t)k * (uint32_t)p.np));
             }
+            {   // ... and the target waypoint (row 4 of the column; observe() reads it before the cursor's first locate)
+                const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&s_coef[4 * D2D_BLOCK + tid]);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(p.wps + base + (uint32_t)(c.n_wps - 1) * (uint32_t)p.np));
+            }
             asm volatile("cp.async.commit_group;" ::: "memory");
         }
 
@@ -309,7 +313,7 @@ __global__ void __launch_bounds__(D2D_BLOCK, D2D_MIN_BLOCKS) d2d_step_kernel(con
         // end conditions, known before the search (see end_bits_of)
         int end_bits;
         {
-            const double2 tgt = v.wp(v.n_wps() - 1);
+            const double2 tgt = PER_ENV ? s_coef[4 * D2D_BLOCK + tid] : v.wp(v.n_wps() - 1);
             end_bits = end_bits_of(c, s, div_const(s.an[0], D2D_PI, c.r_pi), m1to1(tgt.x - s.px[0], 0.0, c.W, c.r_W),
                                    m1to1(tgt.y - s.py[0], 0.0, c.H, c.r_H));
         }
@@ -353,7 +357,8 @@ __global__ void __launch_bounds__(D2D_BLOCK, D2D_MIN_BLOCKS) d2d_step_kernel(con
         };
         ObsAux ax;
         const long long t_scan = clock64();
-        observe(v, c, s, rc0, rs0, nr, put, ax, &s_coef[tid], PER_ENV && p.use_hints);
+        observe(v, c, s, rc0, rs0, nr, put, ax, &s_coef[tid], PER_ENV && p.use_hints,
+                PER_ENV ? &s_coef[4 * D2D_BLOCK + tid] : nullptr);
         // The warp's 32 observation rows are contiguous in the output ([N][27] float32): store them now, coalesced,
         // instead of at block end -- when the outputs live in mapped host memory (d2d_step_host) the PCIe writes
         // then start while reward / swap and the block's slower warps are still running.

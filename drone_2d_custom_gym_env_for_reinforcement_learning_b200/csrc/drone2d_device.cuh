@@ -946,11 +946,12 @@ struct ObsAux {
 
 template <class V, class Put>
 __device__ __forceinline__ void observe(const V &v, const D2dConst &c, EnvState &s, double rc0, double rs0,
-                                        const Nearest &nr, Put put, ObsAux &ax, double2 *coef, bool hinted = false)
+                                        const Nearest &nr, Put put, ObsAux &ax, double2 *coef, bool hinted = false,
+                                        const double2 *tgt_staged = nullptr)
 {
     const double W = c.W, H = c.H;
     const double x = s.px[0], y = s.py[0], alpha = s.an[0];
-    const double2 tgt = v.wp(v.n_wps() - 1);                     // env:316-317
+    const double2 tgt = tgt_staged ? *tgt_staged : v.wp(v.n_wps() - 1);   // env:316-317
     ax.o0 = m1to1(s.vx[0], -1330.0, 2660.0, c.r_vel); put(0, ax.o0);      // env:633-636
     ax.o1 = m1to1(s.vy[0], -1330.0, 2660.0, c.r_vel); put(1, ax.o1);
     put(2, clipd(div_const(s.om[0], 11.7, c.r_omega), -1.0, 1.0));        // env:639-640
