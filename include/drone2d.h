@@ -95,7 +95,9 @@ int d2d_set_scenario(d2d_env *env, int n_wps, const double *wps, const double *u
 /* Curriculum mode, parity/checkpoint use: overwrite the per-env tables from
  * HOST arrays wps [n][D2D_MAX_WPS][2], us [n][D2D_MAX_WPS],
  * xparams/yparams [n][D2D_MAX_WPS][3], n_obs [n], obstacles [n][D2D_MAX_OBS_ENV][3].
- * d2d_get_tables reads them back (what the in-kernel reset generated).  Both sync. */
+ * d2d_get_tables reads them back (what the in-kernel reset generated).  Both sync.
+ * d2d_set_tables also re-derives the path points of the closest-point search's opening
+ * evaluations (the `hint` table of the state block) from the new rows. */
 int d2d_set_tables(d2d_env *env, const double *wps, const double *us, const double *xparams,
                    const double *yparams, const int32_t *n_obs, const double *obstacles);
 int d2d_get_tables(d2d_env *env, double *wps, double *us, double *xparams,
