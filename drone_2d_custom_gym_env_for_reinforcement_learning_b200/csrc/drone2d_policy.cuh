@@ -163,7 +163,7 @@ struct D2dPolicySmem {
     D2dPolicyImage w;
     __half x[2 * D2D_POL_TILE * D2D_POL_K0];      // [hi | lo], 2 x 8 KB
     unsigned char spare[8192];
-    unsigned long long bar[3];
+    unsigned long long bar[4];
     uint32_t tmem_base;
 };
 static_assert(2 * D2D_POL_H * D2D_POL_K0 * 2 + 2 * D2D_POL_TILE * D2D_POL_K0 * 2 + 8192 == 2 * D2D_POL_TILE * D2D_POL_K1 * 2,
@@ -199,6 +199,7 @@ d2d_policy_kernel(const D2dPolicyImage *__restrict__ image, const float *__restr
     D2dPolicySmem &S = *reinterpret_cast<D2dPolicySmem *>(smem_raw);
     const int tid = threadIdx.x, warp = tid >> 5, row = tid & (D2D_POL_TILE - 1), half = tid >> 7;
     const uint32_t bar0 = pol::smem_u32(&S.bar[0]), bar1 = pol::smem_u32(&S.bar[1]), barw = pol::smem_u32(&S.bar[2]);
+    const uint32_t barx = pol::smem_u32(&S.bar[3]);
     const int64_t n_tiles = (n + D2D_POL_TILE - 1) / D2D_POL_TILE;
     constexpr uint32_t W0_BYTES = 2 * D2D_POL_H * D2D_POL_K0 * 2;
 
@@ -208,6 +209,7 @@ d2d_policy_kernel(const D2dPolicyImage *__restrict__ image, const float *__restr
         pol::mbar_init(bar0, 1);
         pol::mbar_init(bar1, 1);
         pol::mbar_init(barw, 1);
+        pol::mbar_init(barx, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         // the 25 KB weight image comes in as ONE bulk copy of the TMA unit, completing on barw
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(barw), "r"((uint32_t)sizeof(D2dPolicyImage)) : "memory");
@@ -224,9 +226,36 @@ d2d_policy_kernel(const D2dPolicyImage *__restrict__ image, const float *__restr
     // step kernel that produces `obs` is still finishing; nothing below may.
     asm volatile("griddepcontrol.wait;" ::: "memory");
     float xr[16];
-    d2d_policy_fetch(obs, n, (int64_t)blockIdx.x * D2D_POL_TILE + row, half, xr);
+    {
+        // The first tile's observations: 128 rows x 27 float32 are 13 824 contiguous bytes -- ONE bulk copy of the TMA unit
+        // into the (still unused) X-lo | spare region instead of 16 scalar loads per thread that each touch 32 different
+        // sectors; every thread then picks its 16 values out of shared memory (row stride 27 words: conflict-free).
+        // A ragged last tile or a base pointer that is not 16-byte aligned takes the scalar path.
+        const int64_t base0 = (int64_t)blockIdx.x * D2D_POL_TILE;
+        constexpr uint32_t RAW_BYTES = D2D_POL_TILE * 27 * 4;
+        static_assert(RAW_BYTES % 16 == 0 && RAW_BYTES <= D2D_POL_TILE * D2D_POL_K0 * 2 + 8192 - 1024, "raw tile fits behind X-hi");
+        float *raw = reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(S.x) + D2D_POL_TILE * D2D_POL_K0 * 2);
+        const bool bulk = base0 + D2D_POL_TILE <= n && (reinterpret_cast<uintptr_t>(obs) & 15) == 0;   // CTA-uniform
+        if (bulk) {
+            if (tid == 0) {
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(barx), "r"(RAW_BYTES) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(pol::smem_u32(raw)),
+                             "l"(obs + base0 * 27), "r"(RAW_BYTES), "r"(barx)
+                             : "memory");
+            }
+            __syncthreads();                     // barx is initialised and armed before anybody polls it
+            pol::mbar_wait(barx, 0);
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
+                const int k = half * 16 + j;
+                xr[j] = (k < 27) ? raw[row * 27 + k] : ((k == 27) ? 1.0f : 0.0f);
+            }
+        } else if (base0 < n) {
+            d2d_policy_fetch(obs, n, base0 + row, half, xr);
+        }
+    }
     pol::tc_fence_before();
-    __syncthreads();
+    __syncthreads();                             // (bulk path: every thread holds its inputs before X-lo is written over the raw tile)
     pol::tc_fence_after();
     pol::mbar_wait(barw, 0);                     // the weight image has landed (every thread reads b1 / w2 / b2 / std from it)
     const uint32_t tmem = S.tmem_base;
