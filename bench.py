@@ -55,11 +55,17 @@ def make_config(envs_per_gpu, world):
 
 
 def kernel_source_hash():
+    """Hash of the CUDA sources with comments and white space removed: identifies the CODE an ncu capture was taken on
+    (a reworded comment does not make a capture stale, a changed statement does)."""
+    import re
     h = hashlib.sha1()
     d = os.path.join(REPO, PKG, "csrc")
     for f in sorted(os.listdir(d)):
         if f.endswith((".cu", ".cuh", ".h")):
-            h.update(open(os.path.join(d, f), "rb").read())
+            src = open(os.path.join(d, f), "r", encoding="utf-8", errors="replace").read()
+            src = re.sub(r"/\*.*?\*/", " ", src, flags=re.S)          # block comments
+            src = re.sub(r"(?m)//[^\n]*$", " ", src)                   # line comments (no string literal of these files holds //)
+            h.update(re.sub(r"\s+", " ", src).encode())
     return h.hexdigest()[:12]
 
 

@@ -521,10 +521,9 @@ struct PathCursor {
 // QPMI2D.get_closest_u (predef_path.py:226-248) = scipy fminbound = bounded Brent
 // (_minimize_scalar_bounded, scipy/optimize/_optimize.py:2289-2440) on
 // [-10, L+10], xatol = 1e-6, maxfun = 500.  Same floating-point operations in the same
-// order as the reference; the control flow is arranged around ONE evaluation site (the
-// initial point is the first trip of the loop); get_closest_position (predef_path.py:251-255)
-// is one more evaluation at the minimiser after the loop (4 selects per trip cheaper than
-// carrying the best point through the loop).
+// order as the reference, in scipy's own loop shape (first evaluation in front of the loop, update
+// rules at its bottom); get_closest_position (predef_path.py:251-255) is one more evaluation at
+// the minimiser after the loop (4 selects per trip cheaper than carrying the best point through it).
 // Every lane runs its own iteration count (typically 10-47).
 // The OPENING of that search does not depend on the query point: the first evaluation is at
 // x0 = a + g (b - a), the second (e = 0: a golden-section step) at x1 = x0 + g (b - x0), and the third is a
