@@ -290,7 +290,9 @@ __global__ void __launch_bounds__(D2D_BLOCK, D2D_MIN_BLOCKS) d2d_step_kernel(con
 
         double rc0, rs0;
         if (!p.skip_physics) {
-            physics_step(s, c, (double)act.x, (double)act.y, rc0, rs0);
+            // the warp's own 32 observation rows (3 456 B, idle until observe()) hold the solver's bias terms (3 072 B)
+            physics_step(s, c, (double)act.x, (double)act.y, rc0, rs0,
+                         reinterpret_cast<double2 *>(&s_obs[(tid & ~31) * D2D_OBS_DIM]) + (tid & 31));
         } else {
             // replay mode (tests): the injected state already is the outcome of space.step
             const double2 sc = sincos2(s.an[0]);

@@ -739,8 +739,11 @@ __device__ __forceinline__ void spawn(EnvState &s, const D2dConst &c, double x, 
 // thrust + cpSpaceStep (env:400-406).  Returns the frame's
 // new rotation (cos, sin) for the collision test / observation.
 // ---------------------------------------------------------------------------
+// `bias_s` (optional): lane-private shared-memory column (element j at bias_s[j * 32]) for the six joints' bias
+// velocities.  ptxas has no registers left for them and otherwise RECOMPUTES them from the positions inside every
+// Gauss-Seidel iteration (36 of its 178 FP64 instructions, on the one phase of the kernel that is FP64-pipe bound).
 __device__ __forceinline__ void physics_step(EnvState &s, const D2dConst &c, double act_l, double act_r,
-                                             double &rc0, double &rs0)
+                                             double &rc0, double &rs0, double2 *bias_s = nullptr)
 {
     const double dt = c.dt;
     // env:400-401 (float64 arithmetic on the float32 action, numpy 1.x promotion)
@@ -783,6 +786,10 @@ __device__ __forceinline__ void physics_step(EnvState &s, const D2dConst &c, dou
     q2x[1] = rc[0] * c.R; q2y[1] = rs[0] * c.R;
     q2x[2] = rc[0] * (c.R + c.d); q2y[2] = rs[0] * (c.R + c.d);
     double k11[6], k12[6], k22[6], bsx[6], bsy[6];
+    // 32-bit shared-window address of the bias column, passed through a (no-op) shuffle so that ptxas keeps it in a
+    // register instead of re-deriving it from S2R inside every iteration (as for PathCursor::caddr)
+    uint32_t bias_a = 0;
+    if (bias_s) bias_a = __shfl_sync(__activemask(), (uint32_t)__cvta_generic_to_shared(bias_s), threadIdx.x & 31);
 #pragma unroll
     for (int j = 0; j < 6; j++) {
         const int m = (j < 3) ? 1 : 2;
@@ -800,6 +807,7 @@ __device__ __forceinline__ void physics_step(EnvState &s, const D2dConst &c, dou
         // bias = -delta / dt (error_bias = 0 -> bias_coef = 1)
         bsx[j] = ((s.px[0] + r2x) - (s.px[m] + r1x)) * c.bias_coef;
         bsy[j] = ((s.py[0] + r2y) - (s.py[m] + r1y)) * c.bias_coef;
+        if (bias_s) asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(bias_a + (uint32_t)(j * 32 * 16)), "d"(bsx[j]), "d"(bsy[j]) : "memory");
     }
 
     // 5. cpBodyUpdateVelocity (space damping 1; env:376-380 has no physical effect)
@@ -842,7 +850,9 @@ __device__ __forceinline__ void physics_step(EnvState &s, const D2dConst &c, dou
             }
             const double vrx = (s.vx[0] - r2y * s.om[0]) - vax;
             const double vry = (s.vy[0] + r2x * s.om[0]) - vay;
-            const double ex = bsx[j] - vrx, ey = bsy[j] - vry;
+            double bx = bsx[j], by = bsy[j];
+            if (bias_s) asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(bx), "=d"(by) : "r"(bias_a + (uint32_t)(j * 32 * 16)) : "memory");
+            const double ex = bx - vrx, ey = by - vry;
             double jx = ex * k11[j] + ey * k12[j];
             double jy = ex * k12[j] + ey * k22[j];
             const double ox = s.jx[j], oy = s.jy[j];
