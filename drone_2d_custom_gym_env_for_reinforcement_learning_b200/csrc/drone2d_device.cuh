@@ -785,6 +785,12 @@ __device__ __forceinline__ void physics_step(EnvState &s, const D2dConst &c, dou
     q2x[0] = rc[0] * (c.R - c.d); q2y[0] = rs[0] * (c.R - c.d);
     q2x[1] = rc[0] * c.R; q2y[1] = rs[0] * c.R;
     q2x[2] = rc[0] * (c.R + c.d); q2y[2] = rs[0] * (c.R + c.d);
+    // Opaque to the optimiser from here on: ptxas otherwise re-derives the lever arms from (cos, sin) and the
+    // constants inside every Gauss-Seidel iteration (an FP64 multiply + add each) to save their registers.
+#pragma unroll
+    for (int k = 0; k < 3; k++) asm volatile("" : "+d"(q2x[k]), "+d"(q2y[k]));
+#pragma unroll
+    for (int k = 0; k < 2; k++) asm volatile("" : "+d"(q1x[k]), "+d"(q1y[k]));
     double k11[6], k12[6], k22[6], bsx[6], bsy[6];
     // 32-bit shared-window address of the bias column, passed through a (no-op) shuffle so that ptxas keeps it in a
     // register instead of re-deriving it from S2R inside every iteration (as for PathCursor::caddr)
